@@ -1,0 +1,177 @@
+/* linnaeus_b200 -- C ABI of the B200 (sm_100a) mFormer hot-path kernels.
+ *
+ * The reference (polli-labs/linnaeus) is pure Python/PyTorch and has no native
+ * interface of its own; each entry point below replaces the chain of PyTorch
+ * library calls at the cited reference location (R/ = /root/reference/linnaeus).
+ * The Python host layer (linnaeus_b200/functional.py) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Contract ("C-ABI layer"):
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the
+ *    caller; the library never allocates, frees or retains pointers;
+ *  - every launch goes to the passed stream, no hidden synchronisation, CUDA-graph
+ *    capturable;
+ *  - returns 0 (LNX_OK) or a negative error code, never aborts or throws.
+ *  - dtype: LNX_F32 = 0, LNX_BF16 = 1 (activations); parameters, statistics,
+ *    gradients of parameters are always float32.
+ *  - "+=" in a comment means the kernel atomically accumulates into the buffer.
+ */
+#ifndef LINNAEUS_B200_H
+#define LINNAEUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lnx_stream_t; /* cudaStream_t */
+
+enum { LNX_F32 = 0, LNX_BF16 = 1 };
+enum {
+  LNX_OK = 0,
+  LNX_ERR_SHAPE = -1,
+  LNX_ERR_DTYPE = -2,
+  LNX_ERR_ALIGN = -3,
+  LNX_ERR_CUDA = -4,
+  LNX_ERR_UNSUPPORTED = -5,
+  LNX_ERR_NULL = -6
+};
+enum { LNX_ACT_NONE = 0, LNX_ACT_GELU = 1, LNX_ACT_RELU = 2 };
+enum { LNX_LOSS_CE = 0, LNX_LOSS_LABEL_SMOOTHING = 1, LNX_LOSS_TAXONOMY = 2 };
+
+int lnx_version(void);
+const char* lnx_strerror(int code);
+
+/* ---- layout ------------------------------------------------------------ */
+/* Stem im2col: x f32 NCHW [B,Cin,H,W] -> out [B*(H/p)*(W/p), Kpad], column order
+ * (c,kh,kw) = Conv2d weight.flatten(1), zero padded to Kpad.
+ * Replaces the input side of nn.Conv2d(k=4,s=4), R/models/mFormerV1.py:145-148. */
+int lnx_patchify_nchw(const float* x, void* out, int B, int Cin, int H, int W, int p, int Kpad, int out_dtype, lnx_stream_t s);
+
+/* NHWC [B,H,W,C] <-> [B*(H/2)*(W/2), 4C] with column order (kh,kw,c) (inverse=1
+ * is the backward scatter).  Input side of the 2x2/s2 downsample conv,
+ * R/models/blocks/convnext.py:104-115. */
+int lnx_space_to_depth(const void* x, void* out, int B, int H, int W, int C, int inverse, int dtype, lnx_stream_t s);
+
+/* tokens[b] = cat(cls[b or broadcast], extras[b], patches[b]) (torch.cat,
+ * R/models/mFormerV1.py:446-465,479-504).  cls_stride = 0 broadcasts one row;
+ * extras may be NULL with n_meta > 0 (rows are zero filled; used by the
+ * backward of lnx_tokens_split). */
+int lnx_tokens_assemble(const void* cls, int64_t cls_stride, const void* extras, const void* patches, void* tokens,
+                        int B, int n_meta, int n_patch, int D, int dtype, lnx_stream_t s);
+/* inverse: any of cls_out [B,D] / extras_out [B,n_meta,D] / patches_out [B,n_patch,D] may be NULL */
+int lnx_tokens_split(const void* tokens, void* cls_out, void* extras_out, void* patches_out,
+                     int B, int n_meta, int n_patch, int D, int dtype, lnx_stream_t s);
+
+/* out[n] += sum_m x[m,n]  (bias / broadcast-parameter gradients) */
+int lnx_colsum(const void* x, float* out, int64_t M, int N, int dtype, lnx_stream_t s);
+int lnx_cast_f32_to_bf16(const float* in, void* out, int64_t n, lnx_stream_t s);
+/* out = dy * act'(pre)  (single-layer Linear+activation backward; act = LNX_ACT_GELU | LNX_ACT_RELU) */
+int lnx_act_bwd(const void* dy, const void* pre, void* out, int64_t n, int act, int dtype, lnx_stream_t s);
+
+/* ---- normalisation ----------------------------------------------------- */
+/* y = LN(x) * w + b (+ residual); biased variance, fp32 statistics saved in
+ * mean/rstd [rows].  nn.LayerNorm (R/models/blocks/convnext.py:77-78,
+ * rope_2d_mhsa.py:546-547,605,634) and LayerNormChannelsFirst (convnext.py:32-43:
+ * the conv trunk is kept NHWC so channels-first LN is a row LN). */
+int lnx_layernorm_fwd(const void* x, const float* w, const float* b, const void* residual, void* y, float* mean, float* rstd,
+                      int64_t rows, int C, float eps, int dtype, lnx_stream_t s);
+/* dx = LN backward; dw[C] += , db[C] += */
+int lnx_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, void* dx,
+                      float* dw, float* db, int64_t rows, int C, int dtype, lnx_stream_t s);
+
+/* ---- depthwise 7x7 (pad 3) on NHWC ------------------------------------- */
+/* w49c is the Conv2d weight [C,1,7,7] transposed to [49,C]; bias may be NULL.
+ * The data gradient is the same call with the taps reversed and bias = NULL.
+ * R/models/blocks/convnext.py:56-58,76. */
+int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, int dtype, lnx_stream_t s);
+/* dw49c[49,C] += , dbias[C] += */
+int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, int dtype, lnx_stream_t s);
+
+/* ---- GEMM with fused epilogue ------------------------------------------ */
+/* acc[m,n] = sum_k A(m,k) * B(n,k)
+ *   a_trans = 0: A stored [M,K] (row pitch lda); 1: stored [K,M]
+ *   b_trans = 0: B stored [N,K] (row pitch ldb); 1: stored [K,N]
+ * v = acc + bias[n]; aux_out[m,n] = v (pre-activation, optional); v = act(v);
+ * if act_grad_in: v = acc * act'(act_grad_in[m,n]);   (backward through act)
+ * v *= col_scale[n]; v += residual[m,n];  C[m,n] = v   (C, aux, residual pitch = N)
+ * accumulate = 1: C is float32 and receives atomic += (split-K weight gradients).
+ * ab_dtype LNX_BF16 runs the tcgen05/TMEM/TMA kernel when the shape allows
+ * (K-pitch multiple of 8, 16-byte aligned bases), else the SIMT kernel;
+ * LNX_F32 always runs the fp32 SIMT kernel (1e-4 parity mode).
+ * Replaces nn.Linear / patchify Conv2d / their autograd (cuBLASLt, cuDNN):
+ * R/models/blocks/convnext.py:60-64,79-86,110; rope_2d_mhsa.py:292,294,432,502;
+ * mlp.py:37-39,61-65; mFormerV1.py:146,316-323; heads/linear_head.py:33-46. */
+int lnx_gemm(int ab_dtype, const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans,
+             void* C, int c_dtype, int M, int N, int K,
+             const float* bias, int act, void* aux_out, const void* act_grad_in,
+             const void* residual, const float* col_scale, int accumulate, int force_simt, lnx_stream_t s);
+
+/* ---- 2-D "RoPE" (cos scaling) and attention ------------------ */
+/* theta[n,h,j] = tx[n]*freqs[0,h,j] + ty[n]*freqs[1,h,j]; cos/sin tables [H*W,heads,half].
+ * R/models/blocks/rope_2d_mhsa.py:56-73,114-155,404-408. */
+int lnx_rope_table(const float* freqs, float* cos_out, float* sin_out, int H, int W, int heads, int half, lnx_stream_t s);
+/* qkv [B,N,3,heads,hd] -> q,k,v [B,heads,N,hd]; image-token (n >= n_extra) pairs of
+ * q,k scaled by cos; q additionally by q_scale.  rope_2d_mhsa.py:432-456. */
+int lnx_rope_qk_fwd(const void* qkv, const float* cos_tab, void* q, void* k, void* v,
+                    int B, int N, int heads, int hd, int n_extra, float q_scale, int dtype, lnx_stream_t s);
+/* dq,dk,dv [B,heads,N,hd] -> dqkv [B,N,3,heads,hd]; dtheta[N_img,heads,hd/2] += */
+int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, const void* qkv, const float* cos_tab, const float* sin_tab,
+                    void* dqkv, float* dtheta, int B, int N, int heads, int hd, int n_extra, float q_scale, int dtype, lnx_stream_t s);
+/* dfreqs[2,heads,half] += sum_n (tx[n], ty[n]) * dtheta[n,h,j] */
+int lnx_rope_freq_grad(const float* dtheta, float* dfreqs, int H, int W, int heads, int half, lnx_stream_t s);
+
+/* softmax(q k^T) v per (batch, head), fp32 softmax; out [B,N,heads*hd]; lse [B,heads,N].
+ * rope_2d_mhsa.py:492-501 (standard path, scale already folded into q). */
+int lnx_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
+                 int B, int heads, int N, int hd, int dtype, int force_simt, lnx_stream_t s);
+/* delta_ws: float [B,heads,N] scratch */
+int lnx_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
+                 void* dq, void* dk, void* dv, float* delta_ws, int B, int heads, int N, int hd, int dtype, int force_simt, lnx_stream_t s);
+
+/* ---- tail ---------------------------------------------------------------- */
+/* out[b,d] = w[0]*a[b,d] + w[1]*c[b,d] + bias[0]   (Conv1d(2->1,k=1), mFormerV1.py:512-524) */
+int lnx_aggregate2_fwd(const void* a, const void* c, const float* w2, const float* bias1, void* out, int64_t B, int D, int dtype, lnx_stream_t s);
+/* da, dc; dw2[2] += ; dbias1[1] += */
+int lnx_aggregate2_bwd(const void* dout, const void* a, const void* c, const float* w2, void* da, void* dc, float* dw2, float* dbias1,
+                       int64_t B, int D, int dtype, lnx_stream_t s);
+
+/* ---- hierarchical masked loss (R/loss/*) ---------------------------------- */
+/* logits [B,Ctot] (all K heads concatenated, class_off[K+1] column offsets, host
+ * array); targets int64 [K,B]; null_flag uint8 [K,B] or NULL (then null = target==0);
+ * keep float [K,B] or NULL: per-sample multiplier (0 drops a null sample = the
+ * reference's coin flips; class weights are folded in here by the host);
+ * soft_mats: K device pointers ([C_k,C_k] rows) for LNX_LOSS_TAXONOMY, host array.
+ * phase1 != 0: every null sample is zeroed (PHASE1_MASK_NULL_LOSS / ignore_index 0).
+ * Outputs: per_sample [K,B] (masked), raw [K,B] (unmasked, for logging), lse [K,B],
+ * sample_w [K,B] (effective multiplier, consumed by lnx_loss_bwd).
+ * basic_loss.py:15-228, taxonomy_label_smoothing.py:219-408, masking.py:19-466. */
+int lnx_loss_fwd(const void* logits, int dtype, int B, int K, const int* class_off, const int64_t* targets,
+                 const uint8_t* null_flag, const float* keep, int kind, float smoothing, const float* const* soft_mats,
+                 int phase1, float* per_sample, float* raw, float* lse, float* sample_w, lnx_stream_t s);
+/* total = sum_k w[k] * sum_i l[k,i] / max(nvalid_k, 1e-6); nvalid_k = #(l != 0), or B
+ * when phase1 (hierarchical_loss.py:241-276,337-340; gradient_weighting.py:301-358).
+ * scale[k] = w[k]/max(nvalid_k,1e-6); task_sum[k] = weighted task loss; nvalid float [K]. */
+int lnx_loss_reduce(const float* per_sample, const float* task_w, int B, int K, int phase1,
+                    float* total, float* scale, float* task_sum, float* nvalid, lnx_stream_t s);
+/* dlogits[i, off_k + c] = gscale[0] * scale[k] * sample_w[k,i] * (sum(T) * softmax_c - T_c) */
+int lnx_loss_bwd(const void* logits, int dtype, int B, int K, const int* class_off, const int64_t* targets,
+                 const float* sample_w, int kind, float smoothing, const float* const* soft_mats,
+                 const float* lse, const float* scale, const float* gscale, void* dlogits, lnx_stream_t s);
+
+/* ---- optimizer (R/train.py:282-313, R/optimizers/build.py:67-106) -------- */
+/* sumsq[0] += sum g^2  (call once per flat buffer, zero sumsq first) */
+int lnx_sumsq(const float* g, int64_t n, float* sumsq, lnx_stream_t s);
+/* norm_out[0] = sqrt(sumsq * gscale^2); coef_out[0] = clip > 0 ? min(1, clip/(norm+1e-6)) : 1 */
+int lnx_clip_coef(const float* sumsq, float gscale, float clip, float* norm_out, float* coef_out, lnx_stream_t s);
+/* AdamW (decoupled decay) on a flat buffer; g is multiplied by gscale*coef[0] first.
+ * step_size = lr/bc1, bc2_sqrt = sqrt(1-b2^t) computed by the caller. */
+int lnx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+              float weight_decay, float bias_corr1, float bias_corr2, float gscale, const float* coef, lnx_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINNAEUS_B200_H */

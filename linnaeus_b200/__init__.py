@@ -1,0 +1,12 @@
+"""linnaeus_b200 -- B200 (sm_100a) native mFormer training / inference hot path.
+
+Public surface (mirrors ``linnaeus.models`` / ``linnaeus.loss`` for this path):
+``build_model(cfg, num_classes, taxonomy_tree)``, ``register_model``, ``create_model``,
+``weighted_hierarchical_loss``, ``FlatAdamW``, ``DataParallel``, ``install_into_linnaeus``.
+"""
+from .config import CfgNode, get_default_config, make_synthetic_config  # noqa: F401
+from .registry import build_model, create_model, install_into_linnaeus, list_models, register_head, register_model  # noqa: F401
+from . import mformer_v1  # noqa: F401  (registers "mFormerV1")
+from .mformer_v1 import mFormerV1  # noqa: F401
+
+__version__ = "0.1.0"

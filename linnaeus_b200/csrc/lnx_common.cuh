@@ -1,0 +1,100 @@
+// Shared device/host helpers for the linnaeus_b200 sm_100a kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/linnaeus_b200.h"
+
+#define LNX_CHECK_LAUNCH()                                \
+  do {                                                    \
+    cudaError_t e__ = cudaGetLastError();                 \
+    if (e__ != cudaSuccess) return lnx_set_cuda_error(e__); \
+  } while (0)
+
+#define LNX_REQUIRE(cond, code) \
+  do {                          \
+    if (!(cond)) return (code); \
+  } while (0)
+
+int lnx_set_cuda_error(cudaError_t e);  // records the CUDA error string, returns LNX_ERR_CUDA
+
+static inline bool lnx_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+namespace lnx {
+
+constexpr int kNumSMs = 148;
+
+typedef __nv_bfloat16 bf16;
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vector of T: 4 floats or 8 bf16
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  float4 raw;
+  __device__ __forceinline__ float get(int i) const { return (&raw.x)[i]; }
+  __device__ __forceinline__ void set(int i, float v) { (&raw.x)[i] = v; }
+};
+template <>
+struct Vec16<bf16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ float get(int i) const {
+    const bf16* p = reinterpret_cast<const bf16*>(&raw);
+    return __bfloat162float(p[i]);
+  }
+  __device__ __forceinline__ void set(int i, float v) {
+    bf16* p = reinterpret_cast<bf16*>(&raw);
+    p[i] = __float2bfloat16_rn(v);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ Vec16<T> ld16(const T* p) {
+  Vec16<T> v;
+  v.raw = *reinterpret_cast<const decltype(v.raw)*>(p);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ void st16(T* p, const Vec16<T>& v) {
+  *reinterpret_cast<decltype(v.raw)*>(p) = v.raw;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// erf-GELU (nn.GELU default) and its derivative
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace lnx

@@ -1,0 +1,43 @@
+// Shared GEMM argument block and the scalar epilogue used by both GEMM kernels.
+#pragma once
+#include "lnx_common.cuh"
+
+struct GemmArgs {
+  const void* A;
+  const void* B;
+  void* C;
+  long long lda, ldb;
+  int M, N, K;
+  int a_trans, b_trans;
+  const float* bias;
+  int act;
+  void* aux_out;
+  const void* act_grad_in;
+  const void* residual;
+  const float* col_scale;
+  int accumulate;
+};
+
+// v = acc -> epilogue value for element (m, n) at flat index idx (pitch N)
+template <typename TC>
+__device__ __forceinline__ float gemm_epilogue_scalar(float v, int n, long long idx, const GemmArgs& g, TC* aux, const TC* agi,
+                                                      const TC* res) {
+  using namespace lnx;
+  if (g.bias) v += g.bias[n];
+  if (aux) aux[idx] = from_f32<TC>(v);
+  if (agi) {
+    const float u = to_f32(agi[idx]);
+    if (g.act == LNX_ACT_GELU) v *= gelu_grad_f(u);
+    else if (g.act == LNX_ACT_RELU) v = (u > 0.f) ? v : 0.f;
+  } else {
+    if (g.act == LNX_ACT_GELU) v = gelu_f(v);
+    else if (g.act == LNX_ACT_RELU) v = fmaxf(v, 0.f);
+  }
+  if (g.col_scale) v *= g.col_scale[n];
+  if (res) v += to_f32(res[idx]);
+  return v;
+}
+
+int lnx_gemm_simt(const GemmArgs& g, int ab_dtype, int c_dtype, cudaStream_t st);
+// returns LNX_ERR_UNSUPPORTED when the shape cannot run on the tcgen05 kernel
+int lnx_gemm_tc(const GemmArgs& g, int c_dtype, cudaStream_t st);

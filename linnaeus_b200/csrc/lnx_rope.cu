@@ -1,0 +1,192 @@
+// 2-D "RoPE" of the reference = cos-scaling of (even, odd) q/k pairs of the image
+// tokens.  Forward splits qkv into head-major q/k/v (the layout the
+// attention kernels read with TMA / coalesced loads) and folds the softmax scale into q.
+// Backward folds the same factors into dqkv and reduces dtheta for the learnable freqs.
+#include "lnx_common.cuh"
+
+using namespace lnx;
+
+namespace {
+
+__global__ void rope_table_kernel(const float* __restrict__ freqs, float* __restrict__ cos_out, float* __restrict__ sin_out, int H,
+                                  int W, int heads, int half) {
+  const int total = H * W * heads * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % half;
+    const int h = (i / half) % heads;
+    const int n = i / (half * heads);
+    const float tx = (float)(n % W), ty = (float)(n / W);
+    const float th = tx * freqs[(0 * heads + h) * half + j] + ty * freqs[(1 * heads + h) * half + j];
+    cos_out[i] = cosf(th);
+    if (sin_out) sin_out[i] = sinf(th);
+  }
+}
+
+// one thread per 8 consecutive head-dim elements (4 pairs) of one (b, n, which, head)
+template <typename T>
+__global__ void rope_qk_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ cos_tab, T* __restrict__ q, T* __restrict__ k,
+                                   T* __restrict__ v, int B, int N, int heads, int hd, int n_extra, float q_scale) {
+  const int chunks = hd / 8;
+  const long long total = (long long)B * N * 3 * heads * chunks;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % chunks);
+    long long r = i / chunks;
+    const int h = (int)(r % heads); r /= heads;
+    const int which = (int)(r % 3); r /= 3;
+    const int n = (int)(r % N);
+    const long long b = r / N;
+    const T* src = qkv + i * 8;
+    float x[8];
+    if (sizeof(T) == 2) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src);
+      const bf16* hh = reinterpret_cast<const bf16*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __bfloat162float(hh[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = to_f32(src[e]);
+    }
+    if (which < 2) {
+      const float sc = (which == 0) ? q_scale : 1.0f;
+      if (n >= n_extra) {
+        const float* ct = cos_tab + ((long long)(n - n_extra) * heads + h) * (hd / 2) + ch * 4;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] *= ct[e >> 1] * sc;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] *= sc;
+      }
+    }
+    T* dst = (which == 0 ? q : which == 1 ? k : v) + (((b * heads + h) * N + n) * hd) + ch * 8;
+    if (sizeof(T) == 2) {
+      uint4 raw;
+      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+      *reinterpret_cast<uint4*>(dst) = raw;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dst[e] = from_f32<T>(x[e]);
+    }
+  }
+}
+
+// grid: (N, batch chunks); thread = (which in {q,k,v}, head, pair-chunk of 4 pairs)
+template <typename T>
+__global__ void rope_qk_bwd_kernel(const T* __restrict__ dq, const T* __restrict__ dk, const T* __restrict__ dv,
+                                   const T* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+                                   T* __restrict__ dqkv, float* __restrict__ dtheta, int B, int N, int heads, int hd, int n_extra,
+                                   float q_scale, int b_per_block) {
+  const int n = blockIdx.x;
+  const int chunks = hd / 8;
+  const int work = 3 * heads * chunks;
+  const int b0 = blockIdx.y * b_per_block, b1 = min(B, b0 + b_per_block);
+  for (int t = threadIdx.x; t < work; t += blockDim.x) {
+    const int ch = t % chunks;
+    const int h = (t / chunks) % heads;
+    const int which = t / (chunks * heads);
+    const bool img = n >= n_extra;
+    float c[4] = {1.f, 1.f, 1.f, 1.f}, sn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (img && which < 2) {
+      const long long o = ((long long)(n - n_extra) * heads + h) * (hd / 2) + ch * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[e] = cos_tab[o + e], sn[e] = sin_tab[o + e];
+    }
+    const float sc = (which == 0) ? q_scale : 1.0f;
+    float dth[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* gsrc = (which == 0 ? dq : which == 1 ? dk : dv);
+    for (int b = b0; b < b1; ++b) {
+      const T* gp = gsrc + ((((long long)b * heads + h) * N + n) * hd) + ch * 8;
+      const long long o = ((((long long)b * N + n) * 3 + which) * heads + h) * hd + ch * 8;
+      float g[8], x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = to_f32(gp[e]);
+      if (which < 2 && img) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = to_f32(qkv[o + e]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dth[e >> 1] += g[e] * x[e] * sc * (-sn[e >> 1]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dqkv[o + e] = from_f32<T>(which < 2 ? g[e] * c[e >> 1] * sc : g[e]);
+    }
+    if (which < 2 && img) {
+      float* dst = dtheta + ((long long)(n - n_extra) * heads + h) * (hd / 2) + ch * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(dst + e, dth[e]);
+    }
+  }
+}
+
+__global__ void rope_freq_grad_kernel(const float* __restrict__ dtheta, float* __restrict__ dfreqs, int H, int W, int heads, int half) {
+  // one thread per (h, j); loops over the grid positions
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= heads * half) return;
+  float gx = 0.f, gy = 0.f;
+  for (int n = 0; n < H * W; ++n) {
+    const float d = dtheta[(long long)n * heads * half + i];
+    gx += (float)(n % W) * d;
+    gy += (float)(n / W) * d;
+  }
+  atomicAdd(dfreqs + i, gx);
+  atomicAdd(dfreqs + heads * half + i, gy);
+}
+
+}  // namespace
+
+extern "C" int lnx_rope_table(const float* freqs, float* cos_out, float* sin_out, int H, int W, int heads, int half, lnx_stream_t s) {
+  LNX_REQUIRE(freqs && cos_out, LNX_ERR_NULL);
+  LNX_REQUIRE(H > 0 && W > 0 && heads > 0 && half > 0, LNX_ERR_SHAPE);
+  const int total = H * W * heads * half;
+  rope_table_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)s>>>(freqs, cos_out, sin_out, H, W, heads, half);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+extern "C" int lnx_rope_qk_fwd(const void* qkv, const float* cos_tab, void* q, void* k, void* v, int B, int N, int heads, int hd,
+                               int n_extra, float q_scale, int dtype, lnx_stream_t s) {
+  LNX_REQUIRE(qkv && cos_tab && q && k && v, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && N > n_extra && heads > 0 && hd % 8 == 0, LNX_ERR_SHAPE);
+  LNX_REQUIRE(lnx_aligned16(qkv) && lnx_aligned16(q) && lnx_aligned16(k) && lnx_aligned16(v), LNX_ERR_ALIGN);
+  const long long total = (long long)B * N * 3 * heads * (hd / 8);
+  const int blocks = (int)min((long long)kNumSMs * 16, (total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)s;
+  if (dtype == LNX_F32)
+    rope_qk_fwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)qkv, cos_tab, (float*)q, (float*)k, (float*)v, B, N, heads, hd, n_extra, q_scale);
+  else if (dtype == LNX_BF16)
+    rope_qk_fwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)qkv, cos_tab, (bf16*)q, (bf16*)k, (bf16*)v, B, N, heads, hd, n_extra, q_scale);
+  else
+    return LNX_ERR_DTYPE;
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+extern "C" int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, const void* qkv, const float* cos_tab, const float* sin_tab,
+                               void* dqkv, float* dtheta, int B, int N, int heads, int hd, int n_extra, float q_scale, int dtype,
+                               lnx_stream_t s) {
+  LNX_REQUIRE(dq && dk && dv && qkv && cos_tab && sin_tab && dqkv && dtheta, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && N > n_extra && heads > 0 && hd % 8 == 0, LNX_ERR_SHAPE);
+  const int work = 3 * heads * (hd / 8);
+  const int threads = min(256, ((work + 31) / 32) * 32);
+  int by = max(1, min(B, (kNumSMs * 8 + N - 1) / N));
+  const int bpb = (B + by - 1) / by;
+  by = (B + bpb - 1) / bpb;
+  dim3 grid(N, by);
+  cudaStream_t st = (cudaStream_t)s;
+  if (dtype == LNX_F32)
+    rope_qk_bwd_kernel<float><<<grid, threads, 0, st>>>((const float*)dq, (const float*)dk, (const float*)dv, (const float*)qkv, cos_tab, sin_tab, (float*)dqkv, dtheta, B, N, heads, hd, n_extra, q_scale, bpb);
+  else if (dtype == LNX_BF16)
+    rope_qk_bwd_kernel<bf16><<<grid, threads, 0, st>>>((const bf16*)dq, (const bf16*)dk, (const bf16*)dv, (const bf16*)qkv, cos_tab, sin_tab, (bf16*)dqkv, dtheta, B, N, heads, hd, n_extra, q_scale, bpb);
+  else
+    return LNX_ERR_DTYPE;
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+extern "C" int lnx_rope_freq_grad(const float* dtheta, float* dfreqs, int H, int W, int heads, int half, lnx_stream_t s) {
+  LNX_REQUIRE(dtheta && dfreqs, LNX_ERR_NULL);
+  const int n = heads * half;
+  rope_freq_grad_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)s>>>(dtheta, dfreqs, H, W, heads, half);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}

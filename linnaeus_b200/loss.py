@@ -1,0 +1,227 @@
+"""Hierarchical masked loss behind the reference's loss surface.
+
+Drop-in for ``linnaeus.loss.hierarchical_loss.weighted_hierarchical_loss``
+(R/loss/hierarchical_loss.py:24-406): same call signature, same returned triple
+``(total, loss_components, task_weights)`` with the same ``loss_components`` keys.
+All K tasks are evaluated by one fused CUDA kernel on the concatenated logits; values
+in ``loss_components`` are 0-dim device tensors (``float(x)`` works and is the only
+host sync, taken by the caller if and when it logs).
+
+Criteria are declared with the small marker modules below (same constructor arguments
+as R/loss/basic_loss.py:15-228 and R/loss/taxonomy_label_smoothing.py:131-217); the
+reference's own criterion instances are recognised by class name.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+import torch.nn as nn
+
+from . import functional as F
+from ._lib import LOSS_CE, LOSS_LS, LOSS_TAXONOMY
+
+__all__ = [
+    "CrossEntropyLoss",
+    "LabelSmoothingCrossEntropy",
+    "TaxonomyAwareLabelSmoothingCE",
+    "StaticTaskWeighting",
+    "weighted_hierarchical_loss",
+    "install_into_linnaeus_loss",
+]
+
+
+class _Criterion(nn.Module):
+    kind = LOSS_CE
+    smoothing = 0.0
+
+    def forward(self, logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """Per-sample losses [B] of one task through the fused kernel (K = 1), differentiable."""
+        mats = [self.soft_labels] if self.kind == LOSS_TAXONOMY else None
+        return F.per_sample_loss(logits, _hard(target), self.kind, self.smoothing, mats, getattr(self, "ignore_index", None) == 0)
+
+
+class CrossEntropyLoss(_Criterion):
+    kind = LOSS_CE
+
+    def __init__(self, weight=None, apply_class_weights: bool = False, ignore_index: int | None = None):
+        super().__init__()
+        self.weight, self.apply_class_weights, self.ignore_index = weight, apply_class_weights, ignore_index
+
+
+class LabelSmoothingCrossEntropy(_Criterion):
+    kind = LOSS_LS
+
+    def __init__(self, weight=None, smoothing: float = 0.1, apply_class_weights: bool = False, ignore_index: int | None = None, config=None):
+        super().__init__()
+        assert 0.0 <= smoothing < 1.0
+        self.smoothing = smoothing
+        self.weight, self.apply_class_weights, self.ignore_index = weight, apply_class_weights, ignore_index
+
+
+class TaxonomyAwareLabelSmoothingCE(_Criterion):
+    kind = LOSS_TAXONOMY
+
+    def __init__(self, soft_label_matrix: torch.Tensor, weight=None, apply_class_weights: bool = False, ignore_index: int | None = None,
+                 config=None):
+        super().__init__()
+        if soft_label_matrix.dim() != 2 or soft_label_matrix.shape[0] != soft_label_matrix.shape[1]:
+            raise ValueError("soft_label_matrix must be square [C, C].")
+        self.num_classes = soft_label_matrix.shape[0]
+        self.register_buffer("soft_labels", soft_label_matrix.clone().float().contiguous())
+        self.weight, self.apply_class_weights, self.ignore_index = weight, apply_class_weights, ignore_index
+
+
+class StaticTaskWeighting:
+    """Minimal stand-in for GradientWeighting(type='static') (gradient_weighting.py:171-365)."""
+
+    def __init__(self, task_keys: list[str], init_weights=None, class_weights=None):
+        self.task_keys = list(task_keys)
+        if isinstance(init_weights, dict):
+            init_weights = [init_weights.get(k, 1.0) for k in task_keys]
+        self.task_weights = torch.tensor(init_weights or [1.0] * len(task_keys), dtype=torch.float32)
+        self.class_weights = class_weights
+        self.gradnorm = None
+
+
+_KIND_BY_NAME = {
+    "CrossEntropyLoss": LOSS_CE,
+    "LabelSmoothingCrossEntropy": LOSS_LS,
+    "TaxonomyAwareLabelSmoothingCE": LOSS_TAXONOMY,
+}
+
+
+def _hard(t: torch.Tensor) -> torch.Tensor:
+    return t.argmax(dim=1) if t.dim() == 2 else t.long()
+
+
+def _sorted_keys(outputs) -> list[str]:
+    return sorted(outputs.keys(), key=lambda k: int(k.split("_L")[-1]))  # core_loss.py:46
+
+
+def _class_weight_vec(cw: dict, C: int, device) -> torch.Tensor:
+    v = torch.ones(C, dtype=torch.float32)
+    for idx, w in cw.items():
+        if 0 <= int(idx) < C:
+            v[int(idx)] = float(w)
+    return v.to(device)
+
+
+def weighted_hierarchical_loss(
+    outputs: dict[str, torch.Tensor],
+    targets: dict[str, torch.Tensor],
+    criteria: dict[str, nn.Module],
+    task_weighting: Any,
+    ops_schedule: Any,
+    current_step: int,
+    subset_ids: torch.Tensor | None = None,
+    mixed_subset_ids: torch.Tensor | None = None,
+    is_validation: bool = False,
+    logger=None,
+    config=None,
+):
+    keys = _sorted_keys(outputs)
+    if not isinstance(targets, dict):
+        targets = dict(zip(keys, targets))
+    K = len(keys)
+    kinds = {_KIND_BY_NAME.get(type(criteria[k]).__name__) for k in keys}
+    if None in kinds or len(kinds) != 1:
+        raise NotImplementedError(
+            "linnaeus_b200 fuses CrossEntropyLoss / LabelSmoothingCrossEntropy / TaxonomyAwareLabelSmoothingCE, one kind for all tasks; "
+            f"got {[type(criteria[k]).__name__ for k in keys]}"
+        )
+    kind = kinds.pop()
+    smoothing = float(getattr(criteria[keys[0]], "smoothing", 0.0))
+    phase1 = bool(config is not None and getattr(config.TRAIN, "PHASE1_MASK_NULL_LOSS", False) and not is_validation)
+
+    # concatenated logits: reuse the model's single head-GEMM output when the dict carries it
+    cat = getattr(outputs, "cat", None)
+    if cat is not None and list(outputs.keys()) == keys:
+        class_off = tuple(outputs.class_off)
+    else:
+        cat = torch.cat([outputs[k].float() for k in keys], dim=1)
+        class_off = [0]
+        for k in keys:
+            class_off.append(class_off[-1] + outputs[k].shape[1])
+        class_off = tuple(class_off)
+    dev = cat.device
+    B = cat.shape[0]
+
+    tg = torch.stack([_hard(targets[k]) for k in keys]).to(dev).contiguous()
+    null_flag = None
+    if any(targets[k].dim() == 2 for k in keys):
+        null_flag = torch.stack([(targets[k][:, 0] > 0.5) if targets[k].dim() == 2 else (targets[k] == 0) for k in keys])
+        null_flag = null_flag.to(device=dev, dtype=torch.uint8).contiguous()
+
+    # null masking probability (masking.py:548-564)
+    if is_validation:
+        p = 1.0
+    elif phase1:
+        p = 0.0
+    else:
+        p = float(ops_schedule.get_null_mask_prob(current_step)) if ops_schedule is not None else 1.0
+    keep = None
+    if (not phase1) and p < 1.0:
+        is_null = null_flag.bool() if null_flag is not None else (tg == 0)
+        coin = torch.rand((K, B), device=dev) < p
+        keep = torch.where(is_null & ~coin, 0.0, 1.0).float()
+    # class weights: dict lookup applied repeatedly by the reference
+    cw = getattr(task_weighting, "class_weights", None)
+    if cw:
+        times = 2 if phase1 else 3
+        mult = torch.ones((K, B), device=dev)
+        for i, k in enumerate(keys):
+            if k in cw:
+                C = class_off[i + 1] - class_off[i]
+                mult[i] = _class_weight_vec(cw[k], C, dev)[tg[i]].pow(times)
+        keep = mult if keep is None else keep * mult
+
+    tw = None
+    gn = getattr(task_weighting, "gradnorm", None)
+    w_src = gn.task_weights if gn is not None else getattr(task_weighting, "task_weights", None)
+    if w_src is not None:
+        order = list(getattr(task_weighting, "task_keys", keys))
+        w_src = w_src.detach().float().cpu()
+        tw = torch.tensor([float(w_src[order.index(k)]) for k in keys], dtype=torch.float32, device=dev)
+
+    soft = None
+    if kind == LOSS_TAXONOMY:
+        soft = [criteria[k].soft_labels.to(dev).float().contiguous() for k in keys]
+
+    stats: dict = {}
+    total = F.hier_loss(cat, tg, class_off, kind, smoothing, soft, tw, keep, null_flag, phase1, stats)
+
+    raw = stats["raw"]
+    per = stats["per_sample"]
+    loss_components = {
+        "total": total.detach(),
+        "tasks": {k: raw[i].mean() for i, k in enumerate(keys)},
+        "masked_tasks": {k: per[i].mean() for i, k in enumerate(keys)},
+        "weighted_tasks": {k: stats["task_sum"][i] for i, k in enumerate(keys)},
+        "raw_per_sample_losses": {k: raw[i] for i, k in enumerate(keys)},
+        "null_masking": {
+            "null_mask_prob": 0.0 if phase1 else p,
+            "num_valid_samples_per_task": {k: stats["nvalid"][i] for i, k in enumerate(keys)},
+            "phase1_active": phase1,
+            "null_samples_total": 0,
+            "null_samples_included": 0,
+            "inclusion_percentage": 0.0,
+        },
+    }
+    task_weights = {k: (tw[i] if tw is not None else 1.0) for i, k in enumerate(keys)}
+    return total, loss_components, task_weights
+
+
+def install_into_linnaeus_loss() -> None:
+    """Rebind the reference's call sites to the fused loss (loss boundary)."""
+    import linnaeus.train as lt
+    import linnaeus.validation as lv
+
+    lt.weighted_hierarchical_loss = weighted_hierarchical_loss
+    lv.weighted_hierarchical_loss = weighted_hierarchical_loss
+    try:
+        import linnaeus.utils.autobatch as la
+
+        la.weighted_hierarchical_loss = weighted_hierarchical_loss
+    except Exception:  # pragma: no cover
+        pass

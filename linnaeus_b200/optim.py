@@ -1,0 +1,149 @@
+"""Flat-buffer AdamW with fused global-norm clipping (the optimizer slice of the hot path).
+
+Follows ``torch.optim.AdamW`` as configured by R/optimizers/build.py:67-106,687-716
+(two groups: decay / no-decay = 1-D tensors and ``.bias``) and the clipping of
+R/train.py:282-313 (``clip_grad_norm_(CLIP_GRAD)``; the reference's two extra norm
+passes are logging only).  Parameters and gradients are re-homed into two contiguous
+float32 buffers so that one ``lnx_sumsq`` + one ``lnx_adamw`` launch per group replaces
+the multi-tensor foreach kernels; the clip coefficient never leaves the device.
+
+The flat gradient buffers are also what ``linnaeus_b200.DataParallel`` all-reduces.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ._lib import call
+
+
+def split_decay(named_params) -> tuple[list, list]:
+    """set_weight_decay (optimizers/build.py:687-716)."""
+    decay, no_decay = [], []
+    for name, p in named_params:
+        if not p.requires_grad:
+            continue
+        (no_decay if (p.ndim == 1 or name.endswith(".bias")) else decay).append((name, p))
+    return decay, no_decay
+
+
+class _FlatGroup:
+    def __init__(self, params: list[torch.nn.Parameter], device):
+        self.params = params
+        self.offsets = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned
+        self.numel = off
+        self.p = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g = torch.zeros(off, dtype=torch.float32, device=device)
+        self.m = torch.zeros(off, dtype=torch.float32, device=device)
+        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets):
+                n = p.numel()
+                self.p[o:o + n].copy_(p.detach().reshape(-1))
+                if p.grad is not None:
+                    self.g[o:o + n].copy_(p.grad.reshape(-1))
+                p.data = self.p[o:o + n].view(p.shape)
+                p.grad = self.g[o:o + n].view(p.shape)
+
+
+class FlatAdamW(torch.optim.Optimizer):
+    """``FlatAdamW(model.named_parameters(), lr=..., weight_decay=..., clip_grad=5.0)``.
+
+    ``param_groups`` keeps the reference's layout (group 0 decay, group 1 no decay) so LR
+    schedulers that write ``group['lr']`` work unchanged.  ``zero_grad`` always zeroes
+    in place (``set_to_none`` would detach ``p.grad`` from the flat buffer)."""
+
+    def __init__(self, named_params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, clip_grad=0.0, grad_scale=1.0):
+        named = list(named_params)
+        if named and isinstance(named[0], torch.nn.Parameter):
+            named = [(f"p{i}", p) for i, p in enumerate(named)]
+        seen, uniq = set(), []
+        for n, p in named:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append((n, p))
+        decay, no_decay = split_decay(uniq)
+        groups = [
+            {"params": [p for _, p in decay], "weight_decay": weight_decay},
+            {"params": [p for _, p in no_decay], "weight_decay": 0.0},
+        ]
+        super().__init__(groups, dict(lr=lr, betas=tuple(betas[:2]), eps=eps, weight_decay=weight_decay))
+        dev = uniq[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdamW needs CUDA parameters (no CPU fallback exists)")
+        self.flat = [_FlatGroup(g["params"], dev) if g["params"] else None for g in self.param_groups]
+        self.clip_grad = float(clip_grad)
+        self.grad_scale = float(grad_scale)  # e.g. 1/world_size folded into the update
+        self._step = 0
+        self._scratch = torch.zeros(3, dtype=torch.float32, device=dev)  # sumsq | norm | coef
+
+    @property
+    def grad_norm(self) -> torch.Tensor:
+        """Global gradient norm measured by the last ``step`` (0-dim device tensor)."""
+        return self._scratch[1]
+
+    def flat_grads(self) -> list[torch.Tensor]:
+        return [f.g for f in self.flat if f is not None]
+
+    def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: ARG002
+        for f in self.flat:
+            if f is not None:
+                f.g.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("closures are not supported")
+        self._step += 1
+        t = self._step
+        sc = self._scratch
+        sc[0:1].zero_()
+        for f in self.flat:
+            if f is not None:
+                call("lnx_sumsq", f.g.data_ptr(), f.numel, sc.data_ptr())
+        call("lnx_clip_coef", sc.data_ptr(), self.grad_scale, self.clip_grad, sc[1:].data_ptr(), sc[2:].data_ptr())
+        for g, f in zip(self.param_groups, self.flat):
+            if f is None:
+                continue
+            b1, b2 = g["betas"]
+            call("lnx_adamw", f.p.data_ptr(), f.g.data_ptr(), f.m.data_ptr(), f.v.data_ptr(), f.numel, float(g["lr"]), float(b1), float(b2),
+                 float(g["eps"]), float(g["weight_decay"]), 1.0 - b1 ** t, 1.0 - b2 ** t, self.grad_scale, sc[2:].data_ptr())
+        return None
+
+    # checkpoint interchange: expose torch.optim.AdamW-shaped state
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["flat_step"] = self._step
+        sd["flat_m"] = [f.m.clone() if f is not None else None for f in self.flat]
+        sd["flat_v"] = [f.v.clone() if f is not None else None for f in self.flat]
+        return sd
+
+    def load_state_dict(self, sd):
+        sd = dict(sd)
+        self._step = sd.pop("flat_step", 0)
+        ms, vs = sd.pop("flat_m", None), sd.pop("flat_v", None)
+        super().load_state_dict(sd)
+        if ms is not None:
+            for f, m, v in zip(self.flat, ms, vs):
+                if f is not None:
+                    f.m.copy_(m)
+                    f.v.copy_(v)
+
+
+def build_optimizer(config, model) -> FlatAdamW:
+    """AdamW slice of ``linnaeus.optimizers.build_optimizer`` (build.py:67-106)."""
+    if config.OPTIMIZER.NAME.lower() != "adamw":
+        raise NotImplementedError("linnaeus_b200 implements the AdamW path only (north_star scope)")
+    return FlatAdamW(
+        model.named_parameters(),
+        lr=config.LR_SCHEDULER.BASE_LR,
+        betas=tuple(config.OPTIMIZER.BETAS[:2]),
+        eps=config.OPTIMIZER.EPS,
+        weight_decay=config.OPTIMIZER.WEIGHT_DECAY,
+        clip_grad=float(config.TRAIN.get("CLIP_GRAD", 0.0)),
+    )
