@@ -167,9 +167,12 @@ int lnx_sumsq(const float* g, int64_t n, float* sumsq, lnx_stream_t s);
 /* norm_out[0] = sqrt(sumsq * gscale^2); coef_out[0] = clip > 0 ? min(1, clip/(norm+1e-6)) : 1 */
 int lnx_clip_coef(const float* sumsq, float gscale, float clip, float* norm_out, float* coef_out, lnx_stream_t s);
 /* AdamW (decoupled decay) on a flat buffer; g is multiplied by gscale*coef[0] first.
- * step_size = lr/bc1, bc2_sqrt = sqrt(1-b2^t) computed by the caller. */
+ * bias_corr{1,2} = 1 - beta^t from the caller, unless step_dev (device float, the
+ * 1-based step count) is given; lr_dev (device float) overrides lr.  The device
+ * variants keep a captured CUDA graph valid across steps. */
 int lnx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-              float weight_decay, float bias_corr1, float bias_corr2, float gscale, const float* coef, lnx_stream_t s);
+              float weight_decay, float bias_corr1, float bias_corr2, float gscale, const float* coef,
+              const float* lr_dev, const float* step_dev, lnx_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,7 @@ SIGNATURES = {
     "lnx_loss_bwd": [P, I, I, I, P, P, P, I, F, P, P, P, P, P, P],
     "lnx_sumsq": [P, L, P, P],
     "lnx_clip_coef": [P, F, F, P, P, P],
-    "lnx_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P, P],
+    "lnx_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P, P, P, P],
 }
 _RESTYPE = {"lnx_strerror": c_char_p}
 

@@ -38,8 +38,14 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float gscale, 
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
-                             const float* __restrict__ coef) {
+                             const float* __restrict__ coef, const float* __restrict__ lr_dev, const float* __restrict__ step_dev) {
   const float gs = gscale * (coef ? coef[0] : 1.0f);
+  if (lr_dev) lr = lr_dev[0];
+  if (step_dev) {  // CUDA-graph replays: the step count lives on the device
+    const float t = step_dev[0];
+    bc1 = 1.0f - powf(b1, t);
+    bc2 = 1.0f - powf(b2, t);
+  }
   const float step = lr / bc1;
   const float inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
   const float decay = 1.0f - lr * wd;
@@ -93,12 +99,13 @@ extern "C" int lnx_clip_coef(const float* sumsq, float gscale, float clip, float
 }
 
 extern "C" int lnx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                         float weight_decay, float bias_corr1, float bias_corr2, float gscale, const float* coef, lnx_stream_t s) {
+                         float weight_decay, float bias_corr1, float bias_corr2, float gscale, const float* coef,
+                         const float* lr_dev, const float* step_dev, lnx_stream_t s) {
   LNX_REQUIRE(p && g && m && v, LNX_ERR_NULL);
   LNX_REQUIRE(n > 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(lnx_aligned16(p) && lnx_aligned16(g) && lnx_aligned16(m) && lnx_aligned16(v), LNX_ERR_ALIGN);
   const int blocks = (int)max(1LL, min((long long)kNumSMs * 8, ((long long)n / 4 + 255) / 256));
-  adamw_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, gscale, coef);
+  adamw_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, gscale, coef, lr_dev, step_dev);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }

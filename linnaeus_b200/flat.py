@@ -1,0 +1,39 @@
+"""Contiguous float32 parameter / gradient buffers (device agnostic; plumbing only).
+
+Parameters are re-homed as views of one flat tensor per group, gradients likewise, so
+the optimizer is two flat launches and data-parallel reduction is a few large
+all-reduces over contiguous slices (reverse-execution-order buckets)."""
+from __future__ import annotations
+
+import torch
+
+
+class FlatGroup:
+    def __init__(self, params: list[torch.nn.Parameter], with_state: bool = True):
+        self.params = list(params)
+        dev = self.params[0].device
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4  # every tensor stays 16-byte aligned
+        self.numel = off
+        self.p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float32, device=dev) if with_state else None
+        self.v = torch.zeros(off, dtype=torch.float32, device=dev) if with_state else None
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                n = p.numel()
+                self.p[o:o + n].copy_(p.detach().reshape(-1))
+                if p.grad is not None:
+                    self.g[o:o + n].copy_(p.grad.reshape(-1))
+                p.data = self.p[o:o + n].view(p.shape)
+                p.grad = self.g[o:o + n].view(p.shape)
+
+    def span(self, i: int) -> tuple[int, int]:
+        return self.offsets[i], self.offsets[i] + self.params[i].numel()
+
+
+def is_flat(p: torch.nn.Parameter, group: FlatGroup, i: int) -> bool:
+    o = group.offsets[i]
+    return p.data_ptr() == group.p.data_ptr() + 4 * o and p.grad is not None and p.grad.data_ptr() == group.g.data_ptr() + 4 * o

@@ -333,8 +333,9 @@ class mFormerV1(nn.Module):
         at the reference's batch sizes)."""
         if not x.is_cuda:
             raise RuntimeError("linnaeus_b200.mFormerV1 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        cd = self._cdtype()  # read before autocast is switched off for the kernels' torch plumbing
         with torch.autocast("cuda", enabled=False):
-            return self._features(x, meta, self._cdtype())
+            return self._features(x, meta, cd)
 
     def _features(self, x, meta, cd):
         B, Cin, Hi, Wi = x.shape

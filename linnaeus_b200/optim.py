@@ -16,6 +16,7 @@ import math
 import torch
 
 from ._lib import call
+from .flat import FlatGroup
 
 
 def split_decay(named_params) -> tuple[list, list]:
@@ -26,29 +27,6 @@ def split_decay(named_params) -> tuple[list, list]:
             continue
         (no_decay if (p.ndim == 1 or name.endswith(".bias")) else decay).append((name, p))
     return decay, no_decay
-
-
-class _FlatGroup:
-    def __init__(self, params: list[torch.nn.Parameter], device):
-        self.params = params
-        self.offsets = []
-        off = 0
-        for p in params:
-            self.offsets.append(off)
-            off += (p.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned
-        self.numel = off
-        self.p = torch.zeros(off, dtype=torch.float32, device=device)
-        self.g = torch.zeros(off, dtype=torch.float32, device=device)
-        self.m = torch.zeros(off, dtype=torch.float32, device=device)
-        self.v = torch.zeros(off, dtype=torch.float32, device=device)
-        with torch.no_grad():
-            for p, o in zip(params, self.offsets):
-                n = p.numel()
-                self.p[o:o + n].copy_(p.detach().reshape(-1))
-                if p.grad is not None:
-                    self.g[o:o + n].copy_(p.grad.reshape(-1))
-                p.data = self.p[o:o + n].view(p.shape)
-                p.grad = self.g[o:o + n].view(p.shape)
 
 
 class FlatAdamW(torch.optim.Optimizer):
@@ -76,11 +54,13 @@ class FlatAdamW(torch.optim.Optimizer):
         dev = uniq[0][1].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdamW needs CUDA parameters (no CPU fallback exists)")
-        self.flat = [_FlatGroup(g["params"], dev) if g["params"] else None for g in self.param_groups]
+        self.flat = [FlatGroup(g["params"]) if g["params"] else None for g in self.param_groups]
         self.clip_grad = float(clip_grad)
         self.grad_scale = float(grad_scale)  # e.g. 1/world_size folded into the update
         self._step = 0
         self._scratch = torch.zeros(3, dtype=torch.float32, device=dev)  # sumsq | norm | coef
+        self._step_dev = torch.zeros(1, dtype=torch.float32, device=dev)  # device-side step count (CUDA-graph safe)
+        self._lr_dev: torch.Tensor | None = None
 
     @property
     def grad_norm(self) -> torch.Tensor:
@@ -89,6 +69,16 @@ class FlatAdamW(torch.optim.Optimizer):
 
     def flat_grads(self) -> list[torch.Tensor]:
         return [f.g for f in self.flat if f is not None]
+
+    def set_device_lr(self, lr: float | None) -> None:
+        """Keep the learning rate in device memory (a captured CUDA graph then follows
+        scheduler updates made with ``set_device_lr`` between replays)."""
+        if lr is None:
+            self._lr_dev = None
+        elif self._lr_dev is None:
+            self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self._scratch.device)
+        else:
+            self._lr_dev.fill_(float(lr))
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: ARG002
         for f in self.flat:
@@ -100,6 +90,7 @@ class FlatAdamW(torch.optim.Optimizer):
         if closure is not None:
             raise NotImplementedError("closures are not supported")
         self._step += 1
+        self._step_dev.add_(1.0)
         t = self._step
         sc = self._scratch
         sc[0:1].zero_()
@@ -112,7 +103,8 @@ class FlatAdamW(torch.optim.Optimizer):
                 continue
             b1, b2 = g["betas"]
             call("lnx_adamw", f.p.data_ptr(), f.g.data_ptr(), f.m.data_ptr(), f.v.data_ptr(), f.numel, float(g["lr"]), float(b1), float(b2),
-                 float(g["eps"]), float(g["weight_decay"]), 1.0 - b1 ** t, 1.0 - b2 ** t, self.grad_scale, sc[2:].data_ptr())
+                 float(g["eps"]), float(g["weight_decay"]), 1.0 - b1 ** t, 1.0 - b2 ** t, self.grad_scale, sc[2:].data_ptr(),
+                 None if self._lr_dev is None else self._lr_dev.data_ptr(), self._step_dev.data_ptr())
         return None
 
     # checkpoint interchange: expose torch.optim.AdamW-shaped state
@@ -126,6 +118,7 @@ class FlatAdamW(torch.optim.Optimizer):
     def load_state_dict(self, sd):
         sd = dict(sd)
         self._step = sd.pop("flat_step", 0)
+        self._step_dev.fill_(float(self._step))
         ms, vs = sd.pop("flat_m", None), sd.pop("flat_v", None)
         super().load_state_dict(sd)
         if ms is not None:

@@ -64,10 +64,10 @@ def test_tc_gemm_epilogues():
     pre = a.float() @ b.float().t() + bias
     assert rel_err(aux, pre) < 1e-2
     assert rel_err(out, TF.gelu(pre) * cs + res.float()) < 1e-2
-    out2 = F.gemm(a, b, M, N, K, act=1, act_grad_in=aux, out_dtype=torch.float32)
+    out2 = F.gemm(a, b, M, N, K, act=1, act_grad_in=aux)  # aux / C share one dtype by contract
     u = aux.float().requires_grad_(True)
     TF.gelu(u).sum().backward()
-    assert rel_err(out2, (a.float() @ b.float().t()) * u.grad) < 1e-5
+    assert rel_err(out2, (a.float() @ b.float().t()) * u.grad) < 1e-2
     out3 = F.gemm(a, b, M, N, K, bias=bias, act=2, out_dtype=torch.float32)
     assert rel_err(out3, TF.relu(pre)) < 1e-5
 

@@ -50,7 +50,7 @@ def _check(name, dtype, rtol):
     total.backward()
     # 1) vs reference golden
     gl = float(z["loss"])
-    assert abs(float(total) - gl) <= rtol * abs(gl), (float(total), gl)
+    assert abs(float(total.detach()) - gl) <= rtol * abs(gl), (float(total.detach()), gl)
     for t, _ in a.tasks:
         ref = torch.from_numpy(z[f"logits/{t}"])
         got = out[t].detach().float().cpu()

@@ -19,6 +19,7 @@ def _F():
 
 def rel_err(a, b):
     a, b = a.float(), b.float()
+    a, b = a.detach(), b.detach()
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
@@ -236,7 +237,8 @@ def test_mlp2_and_linear_autograd(dtype, act, res, cs):
         w1.grad = None
         y2.backward(g2)
         xr2 = x2.detach().float().requires_grad_(True)
-        w1q = w1.detach().clone().requires_grad_(True)
+        # ReLU masks flip on ~0 pre-activations, so the reference uses the same (rounded) weights
+        w1q = w1.detach().to(dtype).float().requires_grad_(True)
         yr2 = TF.relu(TF.linear(xr2, w1q, b1.detach())) + rr2.detach().float()
         yr2.backward(g2.float())
         assert rel_err(y2, yr2) < t and rel_err(x2.grad, xr2.grad) < t and rel_err(w1.grad, w1q.grad) < t
@@ -328,11 +330,12 @@ def test_aggregate_and_colsum():
     out = F.aggregate2(a, c, w, b)
     g = torch.randn_like(out)
     out.backward(g)
-    ar, cr = a.detach().clone().requires_grad_(True), c.detach().clone().requires_grad_(True)
-    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    # CPU reference: cuDNN's conv1d would run in TF32
+    ar, cr = a.detach().cpu().requires_grad_(True), c.detach().cpu().requires_grad_(True)
+    wr, br = w.detach().cpu().requires_grad_(True), b.detach().cpu().requires_grad_(True)
     ref = TF.conv1d(torch.stack([ar, cr], 1), wr, br).squeeze(1)
-    ref.backward(g)
-    assert rel_err(out, ref) < 1e-6 and rel_err(a.grad, ar.grad) < 1e-6 and rel_err(c.grad, cr.grad) < 1e-6
-    assert rel_err(w.grad, wr.grad) < 1e-5 and rel_err(b.grad, br.grad) < 1e-5
+    ref.backward(g.cpu())
+    assert rel_err(out.cpu(), ref) < 1e-6 and rel_err(a.grad.cpu(), ar.grad) < 1e-6 and rel_err(c.grad.cpu(), cr.grad) < 1e-6
+    assert rel_err(w.grad.cpu(), wr.grad) < 1e-5 and rel_err(b.grad.cpu(), br.grad) < 1e-5
     x = torch.randn(1234, 77, device=DEV)
     assert rel_err(F.colsum(x), x.sum(0)) < 1e-5
