@@ -1,0 +1,106 @@
+"""The training step of the hot path (R/train.py:115-377 at accumulation boundaries):
+forward -> hierarchical loss -> backward -> (all-reduce) -> clip -> AdamW -> zero grads.
+
+``TrainStep.step(images, meta, targets)`` is the eager path.  ``capture()`` records the
+whole step into one CUDA graph over static input buffers, which removes the ~1.5 k
+Python/launch overheads per step (the reference's eager loop is launch bound at small
+batch); learning rate and step count then live in device memory so replays stay valid.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import loss as LL
+from .optim import FlatAdamW
+from .parallel import DataParallel
+
+
+class TrainStep:
+    def __init__(self, model, optimizer: FlatAdamW, task_keys: list[str], num_classes: dict[str, int], kind: str = "ce",
+                 smoothing: float = 0.1, soft_matrices: dict | None = None, task_weights: dict | None = None, config=None,
+                 dp: DataParallel | None = None):
+        self.model = model
+        self.opt = optimizer
+        self.keys = list(task_keys)
+        self.config = config
+        self.dp = dp
+        dev = next(model.parameters()).device
+        if kind == "ce":
+            self.criteria = {k: LL.CrossEntropyLoss() for k in self.keys}
+        elif kind == "ls":
+            self.criteria = {k: LL.LabelSmoothingCrossEntropy(smoothing=smoothing) for k in self.keys}
+        elif kind == "taxonomy":
+            self.criteria = {k: LL.TaxonomyAwareLabelSmoothingCE(soft_matrices[k]).to(dev) for k in self.keys}
+        else:
+            raise ValueError(kind)
+        self.weighting = LL.StaticTaskWeighting(self.keys, task_weights)
+        self._graph = None
+        self._static = None
+        self.loss = None
+
+    def _fwd_bwd(self, images, meta, targets: dict):
+        net = self.dp if self.dp is not None else self.model
+        out = net(images, meta)
+        total, comps, _ = LL.weighted_hierarchical_loss(out, targets, self.criteria, self.weighting, None, 0, config=self.config)
+        total.backward()
+        return total.detach()
+
+    def step(self, images, meta, targets: dict) -> torch.Tensor:
+        """One eager optimizer step; returns the (device) loss scalar."""
+        loss = self._fwd_bwd(images, meta, targets)
+        if self.dp is not None:
+            self.dp.finish_gradients()
+        self.opt.step()
+        self.opt.zero_grad()
+        self.loss = loss
+        return loss
+
+    # ---- CUDA graph ---------------------------------------------------------
+    def capture(self, images, meta, targets: dict, warmup: int = 3) -> None:
+        """Capture forward+backward+optimizer into one graph (single-GPU, or the compute part
+        of a data-parallel step: the all-reduce stays outside the graph)."""
+        dev = images.device
+        self._static = (images.clone(), None if meta is None else meta.clone(), {k: v.clone() for k, v in targets.items()})
+        si, sm, st = self._static
+        self.opt.set_device_lr(self.opt.param_groups[0]["lr"])
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._graph_body(si, sm, st)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        from . import _lib
+
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._graph_body(si, sm, st)
+        self.launches_per_step = _lib.launch_count - n0  # C-ABI kernel launches recorded in the graph
+
+    def _graph_body(self, si, sm, st):
+        if self.dp is not None:
+            with self.dp.no_sync():  # collectives stay outside the graph
+                return self._fwd_bwd(si, sm, st)
+        loss = self._fwd_bwd(si, sm, st)
+        if self.dp is None:
+            self.opt.step()
+            self.opt.zero_grad()
+        return loss
+
+    def replay(self, images=None, meta=None, targets: dict | None = None) -> torch.Tensor:
+        si, sm, st = self._static
+        if images is not None:
+            si.copy_(images, non_blocking=True)
+        if meta is not None and sm is not None:
+            sm.copy_(meta, non_blocking=True)
+        if targets is not None:
+            for k, v in targets.items():
+                st[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        if self.dp is not None:
+            self.dp.finish_gradients()
+            self.opt.step()
+            self.opt.zero_grad()
+        self.loss = self._static_loss
+        return self._static_loss

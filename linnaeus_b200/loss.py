@@ -180,9 +180,21 @@ def weighted_hierarchical_loss(
     gn = getattr(task_weighting, "gradnorm", None)
     w_src = gn.task_weights if gn is not None else getattr(task_weighting, "task_weights", None)
     if w_src is not None:
-        order = list(getattr(task_weighting, "task_keys", keys))
-        w_src = w_src.detach().float().cpu()
-        tw = torch.tensor([float(w_src[order.index(k)]) for k in keys], dtype=torch.float32, device=dev)
+        cache = getattr(task_weighting, "_lnx_tw_cache", None) if gn is None else None
+        ck = (str(dev), tuple(keys))
+        if cache is not None and ck in cache:
+            tw = cache[ck]
+        else:
+            order = list(getattr(task_weighting, "task_keys", keys))
+            w_cpu = w_src.detach().float().cpu()
+            tw = torch.tensor([float(w_cpu[order.index(k)]) for k in keys], dtype=torch.float32, device=dev)
+            if gn is None:  # static weights: upload once (keeps the step CUDA-graph capturable)
+                try:
+                    if cache is None:
+                        task_weighting._lnx_tw_cache = {}
+                    task_weighting._lnx_tw_cache[ck] = tw
+                except Exception:
+                    pass
 
     soft = None
     if kind == LOSS_TAXONOMY:

@@ -1,0 +1,133 @@
+"""Single-node data parallelism for the hot path (one process per GPU).
+
+Semantics of the reference's ``DDP(model)`` (R/main.py:936-982): every rank runs the
+same model on its shard of the global batch, the loss is normalised per rank, and the
+parameter gradients are **averaged** across ranks before the optimizer step.
+
+B200-first mechanics: gradients already live in contiguous float32 buffers
+(:mod:`linnaeus_b200.flat`), laid out in parameter-registration order, which is the
+reverse of the order in which backward produces them.  The buffer is cut into buckets;
+a post-accumulate hook on every parameter counts its bucket down, and when the last
+gradient of a bucket has landed the bucket's slice is all-reduced asynchronously
+(NCCL over NVLink/NVSwitch; the collective runs on NCCL's stream, overlapping the rest
+of backward).  The 1/world factor is folded into the optimizer kernel
+(``FlatAdamW.grad_scale``) instead of a separate pass over the gradients.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .flat import FlatGroup
+
+
+class _Bucket:
+    __slots__ = ("group", "lo", "hi", "n_params", "pending", "work")
+
+    def __init__(self, group, lo, hi, n_params):
+        self.group, self.lo, self.hi, self.n_params = group, lo, hi, n_params
+        self.pending = n_params
+        self.work = None
+
+
+def plan_buckets(groups: list[FlatGroup], bucket_bytes: int) -> tuple[list[_Bucket], dict[int, int]]:
+    """Cut each flat group into contiguous buckets of about ``bucket_bytes``; returns the
+    buckets and a map id(param) -> bucket index."""
+    buckets, owner = [], {}
+    cap = max(1, bucket_bytes // 4)
+    for gi, g in enumerate(groups):
+        lo, count = 0, 0
+        for i, p in enumerate(g.params):
+            a, b = g.span(i)
+            end = (b + 3) // 4 * 4
+            count += 1
+            owner[id(p)] = len(buckets)
+            last = i == len(g.params) - 1
+            if end - lo >= cap or last:
+                buckets.append(_Bucket(gi, lo, g.numel if last else end, count))
+                lo, count = end, 0
+    return buckets, owner
+
+
+class DataParallel(nn.Module):
+    """``DataParallel(model, flat_groups)`` -- call ``finish_gradients()`` after backward.
+
+    ``flat_groups`` are the optimizer's :class:`FlatGroup` s (``FlatAdamW.flat``).  With
+    ``average=True`` the reduced buffers are divided by the world size here; pass
+    ``average=False`` when the optimizer folds 1/world (``grad_scale``)."""
+
+    def __init__(self, module: nn.Module, flat_groups: list[FlatGroup], bucket_mb: float = 25.0, process_group=None,
+                 average: bool = True, overlap: bool = True):
+        super().__init__()
+        self.module = module
+        self.groups = [g for g in flat_groups if g is not None]
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.average = average
+        self.overlap = overlap
+        self.require_sync = True
+        self.buckets, self._owner = plan_buckets(self.groups, int(bucket_mb * (1 << 20)))
+        self._hooks = []
+        if self.world > 1 and overlap:
+            for g in self.groups:
+                for p in g.params:
+                    if p.requires_grad:
+                        self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.broadcast_parameters()
+
+    def broadcast_parameters(self) -> None:
+        """Rank 0's parameters to everyone (DDP does the same at construction)."""
+        if self.world > 1:
+            for g in self.groups:
+                dist.broadcast(g.p, src=0, group=self.pg)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    # attribute passthrough so callers touching model.head / .use_checkpoint keep working
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(self.module, name)
+
+    def _launch(self, b: _Bucket) -> None:
+        buf = self.groups[b.group].g[b.lo:b.hi]
+        b.work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
+    def _on_grad(self, p: torch.Tensor) -> None:
+        if not self.require_sync:
+            return
+        b = self.buckets[self._owner[id(p)]]
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch(b)
+
+    def no_sync(self):
+        """Context manager for gradient accumulation micro-batches (reduce on the last one only)."""
+        dp = self
+
+        class _Ctx:
+            def __enter__(self):
+                dp.require_sync = False
+
+            def __exit__(self, *exc):
+                dp.require_sync = True
+
+        return _Ctx()
+
+    def finish_gradients(self) -> None:
+        """Launch whatever has not been reduced yet, wait for all buckets, average."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if b.work is None:
+                self._launch(b)
+        for b in self.buckets:
+            b.work.wait()
+            b.work = None
+            b.pending = b.n_params
+        if self.average:
+            for g in self.groups:
+                g.g.mul_(1.0 / self.world)
