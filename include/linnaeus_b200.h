@@ -127,7 +127,7 @@ int lnx_rope_freq_grad(const float* dtheta, float* dfreqs, int H, int W, int hea
  * rope_2d_mhsa.py:492-501 (standard path, scale already folded into q). */
 int lnx_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
                  int B, int heads, int N, int hd, int dtype, int force_simt, lnx_stream_t s);
-/* delta_ws: float [B,heads,N] scratch */
+/* delta_ws: float scratch of B*heads*N*(hd+1) elements (row deltas + fp32 dQ accumulator) */
 int lnx_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                  void* dq, void* dk, void* dv, float* delta_ws, int B, int heads, int N, int hd, int dtype, int force_simt, lnx_stream_t s);
 

@@ -295,6 +295,8 @@ int lnx_attn_bwd_simt(const void* q, const void* k, const void* v, const void* o
 }
 
 int lnx_attn_fwd_tc(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd, cudaStream_t st);
+int lnx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, float* dq_f32,
+                    void* dk, void* dv, int B, int heads, int N, int hd, cudaStream_t st);
 
 extern "C" int lnx_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd,
                             int dtype, int force_simt, lnx_stream_t s) {
@@ -313,6 +315,15 @@ extern "C" int lnx_attn_bwd(const void* q, const void* k, const void* v, const v
                             lnx_stream_t s) {
   LNX_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv && delta_ws, LNX_ERR_NULL);
   LNX_REQUIRE(B > 0 && heads > 0 && N > 0, LNX_ERR_SHAPE);
-  (void)force_simt;
+  if (dtype == LNX_BF16 && !force_simt && hd == 64) {
+    // tensor-core path: dQ is accumulated in fp32 (two key tiles per head) in the workspace, then cast
+    float* dq32 = delta_ws + (long long)B * heads * N;
+    const long long n = (long long)B * heads * N * hd;
+    cudaError_t e = cudaMemsetAsync(dq32, 0, sizeof(float) * n, (cudaStream_t)s);
+    if (e != cudaSuccess) return lnx_set_cuda_error(e);
+    const int r = lnx_attn_bwd_tc(q, k, v, out, dout, lse, dq32, dk, dv, B, heads, N, hd, (cudaStream_t)s);
+    if (r == LNX_OK) return lnx_cast_f32_to_bf16(dq32, dq, n, s);
+    if (r != LNX_ERR_UNSUPPORTED) return r;
+  }
   return lnx_attn_bwd_simt(q, k, v, out, dout, lse, dq, dk, dv, delta_ws, B, heads, N, hd, dtype, (cudaStream_t)s);
 }

@@ -268,14 +268,14 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
           load8_as_f32<TC>(agi + idx, u);
           if (g.act == LNX_ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] *= gelu_grad_f(u[i]);
+            for (int i = 0; i < 8; ++i) vv[i] *= gelu_grad_fast(u[i]);
           } else if (g.act == LNX_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) vv[i] = u[i] > 0.f ? vv[i] : 0.f;
           }
         } else if (g.act == LNX_ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) vv[i] = gelu_f(vv[i]);
+          for (int i = 0; i < 8; ++i) vv[i] = gelu_fast(vv[i]);
         } else if (g.act == LNX_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);

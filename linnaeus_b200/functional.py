@@ -395,7 +395,7 @@ class _RopeAttention(torch.autograd.Function):
         dout = _c(dout)
         dev = qkv.device
         dqkv_h = torch.empty_like(qkv_h)
-        delta = torch.empty((B, heads, N), dtype=torch.float32, device=dev)
+        delta = torch.empty(B * heads * N * (hd + 1), dtype=torch.float32, device=dev)
         call("lnx_attn_bwd", qkv_h[0].data_ptr(), qkv_h[1].data_ptr(), qkv_h[2].data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
              dqkv_h[0].data_ptr(), dqkv_h[1].data_ptr(), dqkv_h[2].data_ptr(), delta.data_ptr(), B, heads, N, hd, dt(qkv), int(FORCE_SIMT))
         dqkv = torch.empty_like(qkv)
