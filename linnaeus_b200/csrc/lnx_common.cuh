@@ -99,7 +99,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // bf16 resolution) with one MUFU.EX2 and one MUFU.RCP instead of the ~40-instruction erff.
 __device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& ez) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
   ez = __expf(-z * z);  // = exp(-x^2/2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
