@@ -97,6 +97,8 @@ int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias,
  * v = acc + bias[n]; aux_out[m,n] = v (pre-activation, optional); v = act(v);
  * if act_grad_in: v = acc * act'(act_grad_in[m,n]);   (backward through act)
  * v *= col_scale[n]; v += residual[m,n];  C[m,n] = v   (C, aux, residual pitch = N)
+ * colsum_out (nullable, float[N]) += column sums of C (the bias gradient of the layer
+ * below, fused into the persistent tensor-core kernel's epilogue).
  * accumulate = 1: C is float32 and receives atomic += (split-K weight gradients).
  * ab_dtype LNX_BF16 runs the tcgen05/TMEM/TMA kernel when the shape allows
  * (K-pitch multiple of 8, 16-byte aligned bases), else the SIMT kernel;
@@ -107,7 +109,7 @@ int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias,
 int lnx_gemm(int ab_dtype, const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans,
              void* C, int c_dtype, int M, int N, int K,
              const float* bias, int act, void* aux_out, const void* act_grad_in,
-             const void* residual, const float* col_scale, int accumulate, int force_simt, lnx_stream_t s);
+             const void* residual, const float* col_scale, float* colsum_out, int accumulate, int force_simt, lnx_stream_t s);
 
 /* ---- 2-D "RoPE" (cos scaling) and attention ------------------ */
 /* theta[n,h,j] = tx[n]*freqs[0,h,j] + ty[n]*freqs[1,h,j]; cos/sin tables [H*W,heads,half].
@@ -127,7 +129,7 @@ int lnx_rope_freq_grad(const float* dtheta, float* dfreqs, int H, int W, int hea
  * rope_2d_mhsa.py:492-501 (standard path, scale already folded into q). */
 int lnx_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
                  int B, int heads, int N, int hd, int dtype, int force_simt, lnx_stream_t s);
-/* delta_ws: float scratch of B*heads*N*(hd+1) elements (row deltas + fp32 dQ accumulator) */
+/* delta_ws: 16-byte aligned float scratch of B*heads*N*(hd+1) + 4 elements (row deltas + fp32 dQ accumulator) */
 int lnx_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                  void* dq, void* dk, void* dv, float* delta_ws, int B, int heads, int N, int hd, int dtype, int force_simt, lnx_stream_t s);
 

@@ -317,7 +317,7 @@ extern "C" int lnx_attn_bwd(const void* q, const void* k, const void* v, const v
   LNX_REQUIRE(B > 0 && heads > 0 && N > 0, LNX_ERR_SHAPE);
   if (dtype == LNX_BF16 && !force_simt && hd == 64) {
     // tensor-core path: dQ is accumulated in fp32 (two key tiles per head) in the workspace, then cast
-    float* dq32 = delta_ws + (long long)B * heads * N;
+    float* dq32 = delta_ws + (((long long)B * heads * N + 3) / 4) * 4;  // keep the accumulator 16-byte aligned
     const long long n = (long long)B * heads * N * hd;
     cudaError_t e = cudaMemsetAsync(dq32, 0, sizeof(float) * n, (cudaStream_t)s);
     if (e != cudaSuccess) return lnx_set_cuda_error(e);

@@ -9,6 +9,7 @@
 // Split-K (grid.z) + fp32 atomics serves the weight gradients (reduction over tokens).
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "lnx_common.cuh"
 #include "lnx_gemm.cuh"
@@ -397,6 +398,8 @@ int launch_tc(const GemmArgs& g, cudaStream_t st) {
 
 }  // namespace
 
+int lnx_gemm_tc2(const GemmArgs& g, float* colsum_out, cudaStream_t st);
+
 int lnx_gemm_tc(const GemmArgs& g, int c_dtype, cudaStream_t st) {
   // shape gate: TMA needs 16-byte pitches/bases; the vector epilogue needs N % 8 == 0
   if (g.N % 8 != 0 || g.lda % 8 != 0 || g.ldb % 8 != 0) return LNX_ERR_UNSUPPORTED;
@@ -413,7 +416,8 @@ int lnx_gemm_tc(const GemmArgs& g, int c_dtype, cudaStream_t st) {
 // ------------------------------------------------------------------ public dispatcher
 extern "C" int lnx_gemm(int ab_dtype, const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, void* C,
                         int c_dtype, int M, int N, int K, const float* bias, int act, void* aux_out, const void* act_grad_in,
-                        const void* residual, const float* col_scale, int accumulate, int force_simt, lnx_stream_t s) {
+                        const void* residual, const float* col_scale, float* colsum_out, int accumulate, int force_simt,
+                        lnx_stream_t s) {
   LNX_REQUIRE(A && B && C, LNX_ERR_NULL);
   LNX_REQUIRE(M > 0 && N > 0 && K > 0 && lda > 0 && ldb > 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(!(accumulate && (bias || act || aux_out || act_grad_in || residual || col_scale)), LNX_ERR_UNSUPPORTED);
@@ -424,9 +428,17 @@ extern "C" int lnx_gemm(int ab_dtype, const void* A, int64_t lda, int a_trans, c
   g.bias = bias; g.act = act; g.aux_out = aux_out; g.act_grad_in = act_grad_in; g.residual = residual; g.col_scale = col_scale;
   g.accumulate = accumulate ? 1 : 0;
   cudaStream_t st = (cudaStream_t)s;
+  LNX_REQUIRE(!(colsum_out && accumulate), LNX_ERR_UNSUPPORTED);
+  static const bool use_v1 = getenv("LNX_GEMM_V1") != nullptr;
+  int r = LNX_ERR_UNSUPPORTED;
   if (ab_dtype == LNX_BF16 && !force_simt) {
-    const int r = lnx_gemm_tc(g, c_dtype, st);
-    if (r != LNX_ERR_UNSUPPORTED) return r;
+    if (c_dtype == LNX_BF16 && !accumulate && !use_v1) {
+      r = lnx_gemm_tc2(g, colsum_out, st);  // persistent kernel, TMA-store epilogue, fused column sums
+      if (r == LNX_OK) return r;
+    }
+    if (r == LNX_ERR_UNSUPPORTED) r = lnx_gemm_tc(g, c_dtype, st);
   }
-  return lnx_gemm_simt(g, ab_dtype, c_dtype, st);
+  if (r == LNX_ERR_UNSUPPORTED) r = lnx_gemm_simt(g, ab_dtype, c_dtype, st);
+  if (r == LNX_OK && colsum_out) r = lnx_colsum(C, colsum_out, M, N, c_dtype, s);
+  return r;
 }

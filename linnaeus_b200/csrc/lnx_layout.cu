@@ -232,9 +232,65 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
   }
 }
 
+// 16-byte loads: a block owns up to 256 column chunks x a slab of rows; thread = (row-in-pass, chunk)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, long long M, int N,
+                                                         long long rows_per_block) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float red[256 * V];
+  const int cpr = N / V;
+  const int cx0 = blockIdx.x * 256;
+  const int cw = min(256, cpr - cx0);
+  const int rp = 256 / cw;
+  const int rr = threadIdx.x / cw, cc = threadIdx.x % cw;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  if (rr < rp) {
+    const T* px = x + (long long)(cx0 + cc) * V;
+    long long r = r0 + rr;
+    for (; r + 3LL * rp < r1; r += 4LL * rp) {  // 4 independent 16-byte loads in flight
+      const Vec16<T> a = ld16(px + r * N), b = ld16(px + (r + rp) * N), c = ld16(px + (r + 2LL * rp) * N), d = ld16(px + (r + 3LL * rp) * N);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += (a.get(i) + b.get(i)) + (c.get(i) + d.get(i));
+    }
+    for (; r < r1; r += rp) {
+      const Vec16<T> a = ld16(px + r * N);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += a.get(i);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) red[(rr * cw + cc) * V + i] = acc[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cw * V; i += 256) {
+    float t = 0.f;
+    for (int j = 0; j < rp; ++j) t += red[j * cw * V + i];
+    atomicAdd(out + (long long)cx0 * V + i, t);
+  }
+}
+
 extern "C" int lnx_colsum(const void* x, float* out, int64_t M, int N, int dtype, lnx_stream_t s) {
   LNX_REQUIRE(x && out, LNX_ERR_NULL);
   LNX_REQUIRE(M > 0 && N > 0, LNX_ERR_SHAPE);
+  {
+    const int V = dtype == LNX_F32 ? 4 : 8;
+    if ((dtype == LNX_F32 || dtype == LNX_BF16) && N % V == 0 && lnx_aligned16(x)) {
+      const int cpr = N / V;
+      const int gx = (cpr + 255) / 256;
+      const long long Ml = (long long)M;
+      int gy = (int)max(1LL, min((Ml + 255) / 256, (long long)(kNumSMs * 8 + gx - 1) / gx));
+      const long long rpb = (Ml + gy - 1) / gy;
+      gy = (int)((Ml + rpb - 1) / rpb);
+      dim3 grid(gx, gy);
+      if (dtype == LNX_F32) colsum_vec_kernel<float><<<grid, 256, 0, (cudaStream_t)s>>>((const float*)x, out, Ml, N, rpb);
+      else colsum_vec_kernel<bf16><<<grid, 256, 0, (cudaStream_t)s>>>((const bf16*)x, out, Ml, N, rpb);
+      LNX_CHECK_LAUNCH();
+      return LNX_OK;
+    }
+  }
   const int gx = (N + 31) / 32;
   const long long Ml = (long long)M;
   int gy = max(1, min((int)((Ml + 63) / 64), (kNumSMs * 8 + gx - 1) / gx));

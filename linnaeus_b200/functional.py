@@ -42,7 +42,7 @@ def compute_copy(p: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 def gemm(a, b, M, N, K, *, a_trans=False, b_trans=False, lda=None, ldb=None, out=None, out_dtype=None, bias=None, act=ACT_NONE,
-         aux_out=None, act_grad_in=None, residual=None, col_scale=None, accumulate=False):
+         aux_out=None, act_grad_in=None, residual=None, col_scale=None, colsum_out=None, accumulate=False):
     """Raw lnx_gemm call.  ``a``/``b`` share one dtype (f32 or bf16)."""
     if lda is None:
         lda = M if a_trans else K
@@ -51,7 +51,7 @@ def gemm(a, b, M, N, K, *, a_trans=False, b_trans=False, lda=None, ldb=None, out
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype or a.dtype, device=a.device)
     call("lnx_gemm", dt(a), a.data_ptr(), lda, int(a_trans), b.data_ptr(), ldb, int(b_trans), out.data_ptr(), dt(out), M, N, K,
-         ptr(bias), act, ptr(aux_out), ptr(act_grad_in), ptr(residual), ptr(col_scale), int(accumulate), int(FORCE_SIMT))
+         ptr(bias), act, ptr(aux_out), ptr(act_grad_in), ptr(residual), ptr(col_scale), ptr(colsum_out), int(accumulate), int(FORCE_SIMT))
     return out
 
 
@@ -176,7 +176,8 @@ class _Mlp2(torch.autograd.Function):
         else:
             w2_eff = w2c
         # dPre = (dy W2_eff) * act'(pre)   [M, Hd]
-        dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=act, act_grad_in=pre)
+        db1 = torch.zeros(Hd, dtype=torch.float32, device=dy2.device)
+        dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=act, act_grad_in=pre, colsum_out=db1)  # db1 fused in the epilogue
         dw2_raw = wgrad(dy2, h)
         db2_raw = colsum(dy2)
         d_cs = None
@@ -188,7 +189,6 @@ class _Mlp2(torch.autograd.Function):
             dw2, db2 = dw2_raw, db2_raw
         dx = gemm(dpre, w1c, M, K, Hd, b_trans=True, ldb=K).view(xshape) if ctx.needs_input_grad[0] else None
         dw1 = wgrad(dpre, x2)
-        db1 = colsum(dpre)
         return dx, dw1, db1, dw2, db2, None, None, None, d_res, d_cs
 
 
@@ -395,7 +395,7 @@ class _RopeAttention(torch.autograd.Function):
         dout = _c(dout)
         dev = qkv.device
         dqkv_h = torch.empty_like(qkv_h)
-        delta = torch.empty(B * heads * N * (hd + 1), dtype=torch.float32, device=dev)
+        delta = torch.empty(B * heads * N * (hd + 1) + 4, dtype=torch.float32, device=dev)
         call("lnx_attn_bwd", qkv_h[0].data_ptr(), qkv_h[1].data_ptr(), qkv_h[2].data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
              dqkv_h[0].data_ptr(), dqkv_h[1].data_ptr(), dqkv_h[2].data_ptr(), delta.data_ptr(), B, heads, N, hd, dt(qkv), int(FORCE_SIMT))
         dqkv = torch.empty_like(qkv)

@@ -33,7 +33,7 @@ def test_attn_tc_forward_backward(B, heads, N):
         lse = torch.empty(B, heads, N, device=DEV)
         call("lnx_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, heads, N, hd, 1, int(force_simt))
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        ws = torch.empty(B * heads * N * (hd + 1), device=DEV)
+        ws = torch.empty(B * heads * N * (hd + 1) + 4, device=DEV)
         call("lnx_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(),
              dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), B, heads, N, hd, 1, int(force_simt))
         return out, lse, dq, dk, dv
@@ -67,7 +67,7 @@ def test_attn_long_sequence_falls_back_forward_but_tc_backward():
     lse = torch.empty(B, heads, N, device=DEV)
     call("lnx_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, heads, N, hd, 1, 0)
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    ws = torch.empty(B * heads * N * (hd + 1), device=DEV)
+    ws = torch.empty(B * heads * N * (hd + 1) + 4, device=DEV)
     call("lnx_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(),
          dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), B, heads, N, hd, 1, 0)
     qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
