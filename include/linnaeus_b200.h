@@ -68,6 +68,8 @@ int lnx_tokens_split(const void* tokens, void* cls_out, void* extras_out, void* 
 /* out[n] += sum_m x[m,n]  (bias / broadcast-parameter gradients) */
 int lnx_colsum(const void* x, float* out, int64_t M, int N, int dtype, lnx_stream_t s);
 int lnx_cast_f32_to_bf16(const float* in, void* out, int64_t n, lnx_stream_t s);
+/* out[m,:] = x[m,:] * s[m / rows_per_group]  (DropPath backward: per-sample mask on the branch gradient) */
+int lnx_rowscale(const void* x, const float* s, void* out, int64_t M, int N, int rows_per_group, int dtype, lnx_stream_t st);
 /* out = dy * act'(pre)  (single-layer Linear+activation backward; act = LNX_ACT_GELU | LNX_ACT_RELU) */
 int lnx_act_bwd(const void* dy, const void* pre, void* out, int64_t n, int act, int dtype, lnx_stream_t s);
 
@@ -96,7 +98,8 @@ int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias,
  *   b_trans = 0: B stored [N,K] (row pitch ldb); 1: stored [K,N]
  * v = acc + bias[n]; aux_out[m,n] = v (pre-activation, optional); v = act(v);
  * if act_grad_in: v = acc * act'(act_grad_in[m,n]);   (backward through act)
- * v *= col_scale[n]; v += residual[m,n];  C[m,n] = v   (C, aux, residual pitch = N)
+ * v *= col_scale[n]; v *= row_scale[m / rows_per_group] (DropPath mask, optional);
+ * v += residual[m,n];  C[m,n] = v   (C, aux, residual pitch = N)
  * colsum_out (nullable, float[N]) += column sums of C (the bias gradient of the layer
  * below, fused into the persistent tensor-core kernel's epilogue).
  * accumulate = 1: C is float32 and receives atomic += (split-K weight gradients).
@@ -109,7 +112,8 @@ int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias,
 int lnx_gemm(int ab_dtype, const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans,
              void* C, int c_dtype, int M, int N, int K,
              const float* bias, int act, void* aux_out, const void* act_grad_in,
-             const void* residual, const float* col_scale, float* colsum_out, int accumulate, int force_simt, lnx_stream_t s);
+             const void* residual, const float* col_scale, const float* row_scale, int rows_per_group, float* colsum_out,
+             int accumulate, int force_simt, lnx_stream_t s);
 
 /* ---- 2-D "RoPE" (cos scaling) and attention ------------------ */
 /* theta[n,h,j] = tx[n]*freqs[0,h,j] + ty[n]*freqs[1,h,j]; cos/sin tables [H*W,heads,half].

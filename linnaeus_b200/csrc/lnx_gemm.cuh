@@ -15,12 +15,14 @@ struct GemmArgs {
   const void* act_grad_in;
   const void* residual;
   const float* col_scale;
+  const float* row_scale;  // per row-group multiplier (DropPath): row_scale[m / rows_per_group]
+  int rows_per_group;
   int accumulate;
 };
 
 // v = acc -> epilogue value for element (m, n) at flat index idx (pitch N)
 template <typename TC>
-__device__ __forceinline__ float gemm_epilogue_scalar(float v, int n, long long idx, const GemmArgs& g, TC* aux, const TC* agi,
+__device__ __forceinline__ float gemm_epilogue_scalar(float v, int m, int n, long long idx, const GemmArgs& g, TC* aux, const TC* agi,
                                                       const TC* res) {
   using namespace lnx;
   if (g.bias) v += g.bias[n];
@@ -34,6 +36,7 @@ __device__ __forceinline__ float gemm_epilogue_scalar(float v, int n, long long 
     else if (g.act == LNX_ACT_RELU) v = fmaxf(v, 0.f);
   }
   if (g.col_scale) v *= g.col_scale[n];
+  if (g.row_scale) v *= g.row_scale[m / g.rows_per_group];
   if (res) v += to_f32(res[idx]);
   return v;
 }

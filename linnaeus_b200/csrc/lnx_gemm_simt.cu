@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g, int k_
         atomicAdd(reinterpret_cast<float*>(g.C) + idx, v);
         continue;
       }
-      v = gemm_epilogue_scalar<TC>(v, n, idx, g, aux, agi, res);
+      v = gemm_epilogue_scalar<TC>(v, m, n, idx, g, aux, agi, res);
       C[idx] = from_f32<TC>(v);
     }
   }

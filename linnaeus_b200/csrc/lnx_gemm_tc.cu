@@ -286,6 +286,11 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
           vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
           vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
         }
+        if (g.row_scale) {
+          const float rs = g.row_scale[m / g.rows_per_group];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] *= rs;
+        }
         if (res) {
           float r[8];
           load8_as_f32<TC>(res + idx, r);
@@ -416,16 +421,17 @@ int lnx_gemm_tc(const GemmArgs& g, int c_dtype, cudaStream_t st) {
 // ------------------------------------------------------------------ public dispatcher
 extern "C" int lnx_gemm(int ab_dtype, const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, void* C,
                         int c_dtype, int M, int N, int K, const float* bias, int act, void* aux_out, const void* act_grad_in,
-                        const void* residual, const float* col_scale, float* colsum_out, int accumulate, int force_simt,
-                        lnx_stream_t s) {
+                        const void* residual, const float* col_scale, const float* row_scale, int rows_per_group, float* colsum_out,
+                        int accumulate, int force_simt, lnx_stream_t s) {
   LNX_REQUIRE(A && B && C, LNX_ERR_NULL);
   LNX_REQUIRE(M > 0 && N > 0 && K > 0 && lda > 0 && ldb > 0, LNX_ERR_SHAPE);
-  LNX_REQUIRE(!(accumulate && (bias || act || aux_out || act_grad_in || residual || col_scale)), LNX_ERR_UNSUPPORTED);
+  LNX_REQUIRE(!(accumulate && (bias || act || aux_out || act_grad_in || residual || col_scale || row_scale)), LNX_ERR_UNSUPPORTED);
+  LNX_REQUIRE(!row_scale || rows_per_group > 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(!accumulate || c_dtype == LNX_F32, LNX_ERR_DTYPE);
   GemmArgs g;
   g.A = A; g.B = B; g.C = C; g.lda = lda; g.ldb = ldb; g.M = M; g.N = N; g.K = K;
   g.a_trans = a_trans ? 1 : 0; g.b_trans = b_trans ? 1 : 0;
-  g.bias = bias; g.act = act; g.aux_out = aux_out; g.act_grad_in = act_grad_in; g.residual = residual; g.col_scale = col_scale;
+  g.bias = bias; g.act = act; g.aux_out = aux_out; g.act_grad_in = act_grad_in; g.residual = residual; g.col_scale = col_scale; g.row_scale = row_scale; g.rows_per_group = rows_per_group;
   g.accumulate = accumulate ? 1 : 0;
   cudaStream_t st = (cudaStream_t)s;
   LNX_REQUIRE(!(colsum_out && accumulate), LNX_ERR_UNSUPPORTED);

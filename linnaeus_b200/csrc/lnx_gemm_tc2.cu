@@ -219,6 +219,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
               vv[0] *= s0.x; vv[1] *= s0.y; vv[2] *= s0.z; vv[3] *= s0.w;
               vv[4] *= s1.x; vv[5] *= s1.y; vv[6] *= s1.z; vv[7] *= s1.w;
             }
+            if (g.row_scale && row_ok) {
+              const float rs = g.row_scale[m / g.rows_per_group];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] *= rs;
+            }
             if (res && ok) {
               const uint4 raw = *reinterpret_cast<const uint4*>(res + idx);
               const bf16* u = reinterpret_cast<const bf16*>(&raw);

@@ -330,6 +330,37 @@ extern "C" int lnx_cast_f32_to_bf16(const float* in, void* out, int64_t n, lnx_s
   return LNX_OK;
 }
 
+// ---------------------------------------------------------------- row scale (DropPath backward)
+template <typename T>
+__global__ void rowscale_kernel(const T* __restrict__ x, const float* __restrict__ sc, T* __restrict__ out, long long M, int N, int rpg) {
+  constexpr int V = Vec16<T>::N;
+  const int Nv = N / V;
+  const long long total = M * Nv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / Nv;
+    const float f = sc[m / rpg];
+    Vec16<T> v = ld16(x + i * V);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v.set(j, v.get(j) * f);
+    st16(out + i * V, v);
+  }
+}
+
+extern "C" int lnx_rowscale(const void* x, const float* s, void* out, int64_t M, int N, int rows_per_group, int dtype, lnx_stream_t st) {
+  LNX_REQUIRE(x && s && out, LNX_ERR_NULL);
+  LNX_REQUIRE(M > 0 && N > 0 && rows_per_group > 0, LNX_ERR_SHAPE);
+  LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(out), LNX_ERR_ALIGN);
+  const int V = dtype == LNX_F32 ? 4 : 8;
+  LNX_REQUIRE(N % V == 0, LNX_ERR_SHAPE);
+  const long long total = (long long)M * (N / V);
+  const int threads = 256, blocks = (int)min((long long)kNumSMs * 16, (total + threads - 1) / threads);
+  if (dtype == LNX_F32) rowscale_kernel<float><<<blocks, threads, 0, (cudaStream_t)st>>>((const float*)x, s, (float*)out, (long long)M, N, rows_per_group);
+  else if (dtype == LNX_BF16) rowscale_kernel<bf16><<<blocks, threads, 0, (cudaStream_t)st>>>((const bf16*)x, s, (bf16*)out, (long long)M, N, rows_per_group);
+  else return LNX_ERR_DTYPE;
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
 // ---------------------------------------------------------------- activation backward
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ out, long long n, int act) {

@@ -42,7 +42,8 @@ def compute_copy(p: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 
 def gemm(a, b, M, N, K, *, a_trans=False, b_trans=False, lda=None, ldb=None, out=None, out_dtype=None, bias=None, act=ACT_NONE,
-         aux_out=None, act_grad_in=None, residual=None, col_scale=None, colsum_out=None, accumulate=False):
+         aux_out=None, act_grad_in=None, residual=None, col_scale=None, row_scale=None, rows_per_group=0, colsum_out=None,
+         accumulate=False):
     """Raw lnx_gemm call.  ``a``/``b`` share one dtype (f32 or bf16)."""
     if lda is None:
         lda = M if a_trans else K
@@ -51,7 +52,7 @@ def gemm(a, b, M, N, K, *, a_trans=False, b_trans=False, lda=None, ldb=None, out
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype or a.dtype, device=a.device)
     call("lnx_gemm", dt(a), a.data_ptr(), lda, int(a_trans), b.data_ptr(), ldb, int(b_trans), out.data_ptr(), dt(out), M, N, K,
-         ptr(bias), act, ptr(aux_out), ptr(act_grad_in), ptr(residual), ptr(col_scale), ptr(colsum_out), int(accumulate), int(FORCE_SIMT))
+         ptr(bias), act, ptr(aux_out), ptr(act_grad_in), ptr(residual), ptr(col_scale), ptr(row_scale), int(rows_per_group), ptr(colsum_out), int(accumulate), int(FORCE_SIMT))
     return out
 
 
@@ -60,6 +61,13 @@ def colsum(x2d: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     if out is None:
         out = torch.zeros(N, dtype=torch.float32, device=x2d.device)
     call("lnx_colsum", x2d.data_ptr(), out.data_ptr(), M, N, dt(x2d))
+    return out
+
+
+def rowscale(x2d: torch.Tensor, s: torch.Tensor, rows_per_group: int) -> torch.Tensor:
+    M, N = x2d.shape
+    out = torch.empty_like(x2d)
+    call("lnx_rowscale", x2d.data_ptr(), s.data_ptr(), out.data_ptr(), M, N, rows_per_group, dt(x2d))
     return out
 
 
@@ -77,7 +85,7 @@ class _Linear(torch.autograd.Function):
     """y = act(x W^T + b) (+ residual).  nn.Linear (+GELU/ReLU) of the reference."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, weight_c, act, residual, x_ld, out_dtype):
+    def forward(ctx, x, weight, bias, weight_c, act, residual, x_ld, out_dtype, row_scale, rpg):
         K = weight.shape[1]
         N = weight.shape[0]
         lead = x.shape[:-1]
@@ -98,18 +106,22 @@ class _Linear(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         aux = torch.empty((M, N), dtype=out_dtype, device=x2.device) if (act != ACT_NONE and need_grad) else None
         res2 = _c(residual).view(M, N) if residual is not None else None
-        y = gemm(x2, wc_use, M, N, K, lda=lda, out_dtype=out_dtype, bias=bias, act=act, aux_out=aux, residual=res2)
-        ctx.save_for_backward(x2, wc_use, aux)
+        y = gemm(x2, wc_use, M, N, K, lda=lda, out_dtype=out_dtype, bias=bias, act=act, aux_out=aux, residual=res2,
+                 row_scale=row_scale, rows_per_group=rpg)
+        ctx.save_for_backward(x2, wc_use, aux, row_scale)
+        ctx.rpg = rpg
         ctx.meta = (act, lead, K, N, lda, bias is not None, residual is not None, x.shape)
         return y.view(*lead, N) if x_ld is None else y
 
     @staticmethod
     def backward(ctx, dy):
-        x2, wc, aux = ctx.saved_tensors
+        x2, wc, aux, row_scale = ctx.saved_tensors
         act, lead, K, N, lda, has_bias, has_res, xshape = ctx.meta
         M = x2.shape[0]
         dy2 = _c(dy).view(M, N)
         d_res = dy if has_res else None
+        if row_scale is not None:  # DropPath: the branch gradient carries the per-sample mask
+            dy2 = rowscale(dy2, row_scale, ctx.rpg)
         if act == ACT_NONE and dy2.dtype != x2.dtype:  # e.g. float32 logits out of a bf16 trunk
             dy2 = cast_bf16(dy2) if x2.dtype == torch.bfloat16 else dy2.float()
         if act != ACT_NONE:
@@ -128,11 +140,11 @@ class _Linear(torch.autograd.Function):
             dw = wgrad(dpre_w, x2, x_ld=lda)
         if has_bias and ctx.needs_input_grad[2]:
             db = colsum(dpre)
-        return dx, dw, db, None, None, d_res, None, None
+        return dx, dw, db, None, None, d_res, None, None, None, None
 
 
-def linear(x, weight, bias=None, weight_c=None, act=None, residual=None, x_ld=None, out_dtype=None):
-    return _Linear.apply(x, weight, bias, weight_c, _ACT[act], residual, x_ld, out_dtype)
+def linear(x, weight, bias=None, weight_c=None, act=None, residual=None, x_ld=None, out_dtype=None, row_scale=None, rows_per_group=0):
+    return _Linear.apply(x, weight, bias, weight_c, _ACT[act], residual, x_ld, out_dtype, row_scale, rows_per_group)
 
 
 # --------------------------------------------------------------------------- two-layer MLP
@@ -145,7 +157,7 @@ class _Mlp2(torch.autograd.Function):
     dgamma = rowsum(dW2_raw * W2) + b2 * db2_raw  (no extra pass over activations)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, w1c, w2c, act, residual, col_scale):
+    def forward(ctx, x, w1, b1, w2, b2, w1c, w2c, act, residual, col_scale, row_scale, rpg):
         K = w1.shape[1]
         Hd = w1.shape[0]
         N = w2.shape[0]
@@ -158,18 +170,21 @@ class _Mlp2(torch.autograd.Function):
         pre = torch.empty((M, Hd), dtype=x2.dtype, device=x2.device) if need_grad else None
         h = gemm(x2, w1c, M, Hd, K, bias=b1, act=act, aux_out=pre)
         res2 = _c(residual).view(M, N) if residual is not None else None
-        y = gemm(h, w2c, M, N, Hd, bias=b2, residual=res2, col_scale=col_scale)
-        ctx.save_for_backward(x2, w1c, w2c, pre, h, col_scale, w2, b2)
+        y = gemm(h, w2c, M, N, Hd, bias=b2, residual=res2, col_scale=col_scale, row_scale=row_scale, rows_per_group=rpg)
+        ctx.save_for_backward(x2, w1c, w2c, pre, h, col_scale, w2, b2, row_scale)
+        ctx.rpg = rpg
         ctx.meta = (act, lead, K, Hd, N, residual is not None, x.shape)
         return y.view(*lead, N)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w1c, w2c, pre, h, col_scale, w2, b2 = ctx.saved_tensors
+        x2, w1c, w2c, pre, h, col_scale, w2, b2, row_scale = ctx.saved_tensors
         act, lead, K, Hd, N, has_res, xshape = ctx.meta
         M = x2.shape[0]
         dy2 = _c(dy).view(M, N)
         d_res = dy if has_res else None
+        if row_scale is not None:  # DropPath: the branch gradient carries the per-sample mask
+            dy2 = rowscale(dy2, row_scale, ctx.rpg)
         if col_scale is not None:
             # fold the layer scale into the weight seen by the data-gradient GEMM
             w2_eff = compute_copy(w2.detach() * col_scale.detach()[:, None], dy2.dtype)
@@ -189,11 +204,11 @@ class _Mlp2(torch.autograd.Function):
             dw2, db2 = dw2_raw, db2_raw
         dx = gemm(dpre, w1c, M, K, Hd, b_trans=True, ldb=K).view(xshape) if ctx.needs_input_grad[0] else None
         dw1 = wgrad(dpre, x2)
-        return dx, dw1, db1, dw2, db2, None, None, None, d_res, d_cs
+        return dx, dw1, db1, dw2, db2, None, None, None, d_res, d_cs, None, None
 
 
-def mlp2(x, w1, b1, w2, b2, w1c=None, w2c=None, act="gelu", residual=None, col_scale=None):
-    return _Mlp2.apply(x, w1, b1, w2, b2, w1c, w2c, _ACT[act], residual, col_scale)
+def mlp2(x, w1, b1, w2, b2, w1c=None, w2c=None, act="gelu", residual=None, col_scale=None, row_scale=None, rows_per_group=0):
+    return _Mlp2.apply(x, w1, b1, w2, b2, w1c, w2c, _ACT[act], residual, col_scale, row_scale, rows_per_group)
 
 
 # --------------------------------------------------------------------------- LayerNorm

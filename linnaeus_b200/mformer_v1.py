@@ -41,6 +41,15 @@ class LayerNormChannelsFirst(nn.Module):
         self.eps = eps
 
 
+def drop_path_mask(B: int, drop_prob: float, training: bool, device) -> torch.Tensor | None:
+    """Per-sample stochastic-depth multiplier floor(keep + U[0,1)) / keep (drop_path.py:11-36); None when inactive.
+    The multiplier is applied inside the epilogue of the GEMM that closes the residual branch."""
+    if drop_prob == 0.0 or not training:
+        return None
+    keep = 1.0 - drop_prob
+    return torch.floor(keep + torch.rand(B, device=device, dtype=torch.float32)) / keep
+
+
 class ConvNeXtBlock(nn.Module):
     """dw7x7 -> LN -> Linear 4x -> GELU -> Linear -> gamma -> + x  (convnext.py:46-100), NHWC."""
 
@@ -57,8 +66,9 @@ class ConvNeXtBlock(nn.Module):
         C = x.shape[-1]
         t = F.dwconv7(x.view(B, H, W, C), self.dwconv.weight, self.dwconv.bias)
         t = F.layernorm(t.view(-1, C), self.norm.weight, self.norm.bias, 1e-6)
+        mask = drop_path_mask(B, self.drop_prob, self.training, x.device)
         return F.mlp2(t, self.pwconv1.weight, self.pwconv1.bias, self.pwconv2.weight, self.pwconv2.bias,
-                      act="gelu", residual=x, col_scale=self.gamma)
+                      act="gelu", residual=x, col_scale=self.gamma, row_scale=mask, rows_per_group=H * W)
 
 
 class ConvNeXtDownsampleLayer(nn.Module):
@@ -120,9 +130,13 @@ class RoPE2DMHSABlock(nn.Module):
         t = F.layernorm(x, self.norm1.weight, self.norm1.bias, 1e-5)
         qkv = F.linear(t, a.qkv.weight, a.qkv.bias)
         o = F.rope_attention(qkv, a.freqs, H, W, a.num_heads, self.extra_token_num)
-        x = F.linear(o, a.proj.weight, a.proj.bias, residual=x)
+        B, N = x.shape[0], x.shape[1]
+        m1 = drop_path_mask(B, self.drop_prob, self.training, x.device)
+        x = F.linear(o, a.proj.weight, a.proj.bias, residual=x, row_scale=m1, rows_per_group=N)
         t = F.layernorm(x, self.norm2.weight, self.norm2.bias, 1e-5)
-        return F.mlp2(t, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, act="gelu", residual=x)
+        m2 = drop_path_mask(B, self.drop_prob, self.training, x.device)
+        return F.mlp2(t, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, act="gelu", residual=x,
+                      row_scale=m2, rows_per_group=N)
 
 
 class ResNormLayer(nn.Module):
