@@ -96,17 +96,27 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 // Fast erf-GELU for the bf16 tensor-core epilogues: Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below
-// bf16 resolution) with one MUFU.EX2 and one MUFU.RCP instead of the ~40-instruction erff.
+// bf16 resolution) with one MUFU.EX2 and one MUFU.RCP issued as raw approx instructions (the CUDA
+// intrinsics add range-fixup code that triples the instruction count of the epilogue).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& ez) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  ez = __expf(-z * z);  // = exp(-x^2/2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erfc_half = 0.5f * poly * t * ez;        // 0.5 * erfc(|x|/sqrt2)
-  cdf = x >= 0.f ? 1.0f - erfc_half : erfc_half;       // Phi(x)
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  ez = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));  // exp(-x^2/2)
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float q = poly * t * ez;            // 0.5 * erfc(|x|/sqrt2)
+  cdf = x >= 0.f ? 1.0f - q : q;            // Phi(x)
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   float cdf, ez;

@@ -31,7 +31,39 @@ extern "C" const char* lnx_strerror(int code) {
 }
 
 // ---------------------------------------------------------------- patchify
-// one thread per output element; reads are p-element runs (16 B for p=4), writes coalesced
+// Thread = (output row, 4-column group): 16 groups per row when Kpad = 64.  A group is one (c, kh) run of p = 4
+// pixels = one aligned 16-byte load from the NCHW image; the 16 threads of a row write one full 128-byte line.
+template <typename T>
+__global__ void patchify4_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int Cin, int H, int W, int Kpad) {
+  const int Ho = H / 4, Wo = W / 4;
+  const int gpr = Kpad / 4;  // groups per output row
+  const int K4 = Cin * 4;    // valid groups: (c, kh)
+  const long long total = (long long)B * Ho * Wo * gpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(i % gpr);
+    const long long row = i / gpr;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gidx < K4) {
+      const int kh = gidx & 3, c = gidx >> 2;
+      const int ow = (int)(row % Wo);
+      const int oh = (int)((row / Wo) % Ho);
+      const int b = (int)(row / ((long long)Wo * Ho));
+      v = *reinterpret_cast<const float4*>(x + (((long long)b * Cin + c) * H + (oh * 4 + kh)) * W + ow * 4);
+    }
+    T* dst = out + row * Kpad + gidx * 4;
+    if (sizeof(T) == 2) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), bq = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&bq);
+      *reinterpret_cast<uint2*>(dst) = o;
+    } else {
+      *reinterpret_cast<float4*>(dst) = v;
+    }
+  }
+}
+
+// generic fallback: one thread per output element
 template <typename T>
 __global__ void patchify_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int Cin, int H, int W, int p, int Kpad) {
   const int Ho = H / p, Wo = W / p;
@@ -55,10 +87,18 @@ __global__ void patchify_kernel(const float* __restrict__ x, T* __restrict__ out
 extern "C" int lnx_patchify_nchw(const float* x, void* out, int B, int Cin, int H, int W, int p, int Kpad, int out_dtype, lnx_stream_t s) {
   LNX_REQUIRE(x && out, LNX_ERR_NULL);
   LNX_REQUIRE(B > 0 && Cin > 0 && p > 0 && H % p == 0 && W % p == 0 && Kpad >= Cin * p * p, LNX_ERR_SHAPE);
-  const long long total = (long long)B * (H / p) * (W / p) * Kpad;
   const int threads = 256;
-  const int blocks = (int)min((long long)kNumSMs * 16, (total + threads - 1) / threads);
   cudaStream_t st = (cudaStream_t)s;
+  if (p == 4 && Kpad % 4 == 0 && W % 4 == 0 && lnx_aligned16(x) && lnx_aligned16(out) && (out_dtype == LNX_F32 || out_dtype == LNX_BF16)) {
+    const long long total = (long long)B * (H / 4) * (W / 4) * (Kpad / 4);
+    const int blocks = (int)min((long long)kNumSMs * 16, (total + threads - 1) / threads);
+    if (out_dtype == LNX_F32) patchify4_kernel<float><<<blocks, threads, 0, st>>>(x, (float*)out, B, Cin, H, W, Kpad);
+    else patchify4_kernel<bf16><<<blocks, threads, 0, st>>>(x, (bf16*)out, B, Cin, H, W, Kpad);
+    LNX_CHECK_LAUNCH();
+    return LNX_OK;
+  }
+  const long long total = (long long)B * (H / p) * (W / p) * Kpad;
+  const int blocks = (int)min((long long)kNumSMs * 16, (total + threads - 1) / threads);
   if (out_dtype == LNX_F32)
     patchify_kernel<float><<<blocks, threads, 0, st>>>(x, (float*)out, B, Cin, H, W, p, Kpad);
   else if (out_dtype == LNX_BF16)

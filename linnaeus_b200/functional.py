@@ -56,6 +56,25 @@ def gemm(a, b, M, N, K, *, a_trans=False, b_trans=False, lda=None, ldb=None, out
     return out
 
 
+# Parameter gradients are accumulated straight into an existing float32 ``param.grad`` (e.g. the views of
+# FlatAdamW's flat buffer) instead of being returned to autograd: no per-tensor zero-fill + add launches.
+DIRECT_GRAD = True
+
+
+def _sink(param):
+    if (DIRECT_GRAD and isinstance(param, torch.nn.Parameter) and param.grad is not None and param.grad.dtype == torch.float32
+            and param.grad.is_contiguous()):
+        return param.grad
+    return None
+
+
+def _grad_done(param) -> None:
+    """Tell a data-parallel wrapper that this parameter's gradient is final (replaces the autograd hook)."""
+    h = getattr(param, "_lnx_grad_ready", None)
+    if h is not None:
+        h(param)
+
+
 def colsum(x2d: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
     M, N = x2d.shape
     if out is None:
@@ -71,11 +90,11 @@ def rowscale(x2d: torch.Tensor, s: torch.Tensor, rows_per_group: int) -> torch.T
     return out
 
 
-def wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, x_ld: int | None = None) -> torch.Tensor:
-    """dW[N,K] = dy[M,N]^T x[M,K], float32, split over M with atomic accumulation."""
+def wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, x_ld: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """dW[N,K] (+)= dy[M,N]^T x[M,K], float32, split over M with atomic accumulation (into ``out`` when given)."""
     M, N = dy2d.shape
     K = x2d.shape[1]
-    dw = torch.zeros((N, K), dtype=torch.float32, device=dy2d.device)
+    dw = out if out is not None else torch.zeros((N, K), dtype=torch.float32, device=dy2d.device)
     gemm(dy2d, x2d, N, K, M, a_trans=True, b_trans=True, lda=N, ldb=x_ld or K, out=dw, accumulate=True)
     return dw
 
@@ -110,6 +129,7 @@ class _Linear(torch.autograd.Function):
                  row_scale=row_scale, rows_per_group=rpg)
         ctx.save_for_backward(x2, wc_use, aux, row_scale)
         ctx.rpg = rpg
+        ctx.params = (weight, bias)
         ctx.meta = (act, lead, K, N, lda, bias is not None, residual is not None, x.shape)
         return y.view(*lead, N) if x_ld is None else y
 
@@ -136,10 +156,21 @@ class _Linear(torch.autograd.Function):
             dpre_w = dpre
         if ctx.needs_input_grad[0]:
             dx = gemm(dpre_w, wc, M, K, N, b_trans=True, ldb=K).view(xshape)
+        weight, bias = ctx.params
         if ctx.needs_input_grad[1]:
-            dw = wgrad(dpre_w, x2, x_ld=lda)
+            sw = _sink(weight)
+            if sw is not None:
+                wgrad(dpre_w, x2, x_ld=lda, out=sw.view(N, K))
+                _grad_done(weight)
+            else:
+                dw = wgrad(dpre_w, x2, x_ld=lda)
         if has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dpre)
+            sb = _sink(bias)
+            if sb is not None:
+                colsum(dpre, out=sb)
+                _grad_done(bias)
+            else:
+                db = colsum(dpre)
         return dx, dw, db, None, None, d_res, None, None, None, None
 
 
@@ -173,6 +204,7 @@ class _Mlp2(torch.autograd.Function):
         y = gemm(h, w2c, M, N, Hd, bias=b2, residual=res2, col_scale=col_scale, row_scale=row_scale, rows_per_group=rpg)
         ctx.save_for_backward(x2, w1c, w2c, pre, h, col_scale, w2, b2, row_scale)
         ctx.rpg = rpg
+        ctx.params = (w1, b1, w2, b2, col_scale)
         ctx.meta = (act, lead, K, Hd, N, residual is not None, x.shape)
         return y.view(*lead, N)
 
@@ -191,19 +223,42 @@ class _Mlp2(torch.autograd.Function):
         else:
             w2_eff = w2c
         # dPre = (dy W2_eff) * act'(pre)   [M, Hd]
-        db1 = torch.zeros(Hd, dtype=torch.float32, device=dy2.device)
+        p_w1, p_b1, p_w2, p_b2, p_cs = ctx.params
+        s_w1, s_b1, s_w2, s_b2 = _sink(p_w1), _sink(p_b1), _sink(p_w2), _sink(p_b2)
+        db1 = s_b1 if s_b1 is not None else torch.zeros(Hd, dtype=torch.float32, device=dy2.device)
         dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=act, act_grad_in=pre, colsum_out=db1)  # db1 fused in the epilogue
-        dw2_raw = wgrad(dy2, h)
-        db2_raw = colsum(dy2)
-        d_cs = None
+        d_cs = dw2 = db2 = None
         if col_scale is not None:
+            dw2_raw = wgrad(dy2, h)
+            db2_raw = colsum(dy2)
+            cs = col_scale.detach()
             d_cs = (dw2_raw * w2.detach()).sum(1) + b2.detach() * db2_raw
-            dw2 = dw2_raw * col_scale.detach()[:, None]
-            db2 = db2_raw * col_scale.detach()
+            if s_w2 is not None:
+                s_w2.view(N, Hd).addcmul_(dw2_raw, cs[:, None])
+                s_b2.addcmul_(db2_raw, cs)
+            else:
+                dw2, db2 = dw2_raw * cs[:, None], db2_raw * cs
+            s_cs = _sink(p_cs)
+            if s_cs is not None:
+                s_cs.add_(d_cs)
+                _grad_done(p_cs)
+                d_cs = None
+        elif s_w2 is not None:
+            wgrad(dy2, h, out=s_w2.view(N, Hd))
+            colsum(dy2, out=s_b2)
         else:
-            dw2, db2 = dw2_raw, db2_raw
+            dw2, db2 = wgrad(dy2, h), colsum(dy2)
         dx = gemm(dpre, w1c, M, K, Hd, b_trans=True, ldb=K).view(xshape) if ctx.needs_input_grad[0] else None
-        dw1 = wgrad(dpre, x2)
+        dw1 = None
+        if s_w1 is not None:
+            wgrad(dpre, x2, out=s_w1.view(Hd, K))
+        else:
+            dw1 = wgrad(dpre, x2)
+        if s_b1 is not None:
+            db1 = None
+        for prm, snk in ((p_w1, s_w1), (p_b1, s_b1), (p_w2, s_w2), (p_b2, s_b2)):
+            if snk is not None:
+                _grad_done(prm)
         return dx, dw1, db1, dw2, db2, None, None, None, d_res, d_cs, None, None
 
 
@@ -225,6 +280,7 @@ class _LayerNorm(torch.autograd.Function):
         call("lnx_layernorm_fwd", x2.data_ptr(), w.data_ptr(), b.data_ptr(), ptr(res2), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
              rows, C, float(eps), dt(x2))
         ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.params = (w, b)
         ctx.has_res = residual is not None
         ctx.xshape = x.shape
         return y.view(x.shape)
@@ -235,10 +291,17 @@ class _LayerNorm(torch.autograd.Function):
         rows, C = x2.shape
         dy2 = _c(dy).view(rows, C)
         dx = torch.empty_like(x2)
-        dw = torch.zeros(C, dtype=torch.float32, device=x2.device)
-        db = torch.zeros(C, dtype=torch.float32, device=x2.device)
+        p_w, p_b = ctx.params
+        s_w, s_b = _sink(p_w), _sink(p_b)
+        direct = s_w is not None and s_b is not None
+        dw = s_w if direct else torch.zeros(C, dtype=torch.float32, device=x2.device)
+        db = s_b if direct else torch.zeros(C, dtype=torch.float32, device=x2.device)
         call("lnx_layernorm_bwd", dy2.data_ptr(), x2.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
              dw.data_ptr(), db.data_ptr(), rows, C, dt(x2))
+        if direct:
+            _grad_done(p_w)
+            _grad_done(p_b)
+            dw = db = None
         return dx.view(ctx.xshape), dw, db, None, (dy if ctx.has_res else None)
 
 

@@ -74,6 +74,7 @@ class DataParallel(nn.Module):
                 for p in g.params:
                     if p.requires_grad:
                         self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+                        p._lnx_grad_ready = self._on_grad  # kernels that write p.grad directly bypass the autograd hook
         self.broadcast_parameters()
 
     def broadcast_parameters(self) -> None:

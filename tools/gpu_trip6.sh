@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+bash tools/run_gpu_checks.sh tests/test_gpu_gemm_tc.py tests/test_gpu_ops.py tests/test_gpu_droppath.py tests/test_gpu_model.py
+python tools/prof_gemm.py 256 > gpurun_out/prof_gemm.log 2>&1; cat gpurun_out/prof_gemm.log
+timeout 600 python bench.py --steps 5 --warmup 2 --batch 256 --no-cpu-baseline > gpurun_out/bench_graph_b256.log 2>&1; echo "graph b256 rc $?"; tail -1 gpurun_out/bench_graph_b256.log | cut -c1-300
