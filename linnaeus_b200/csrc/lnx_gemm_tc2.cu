@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gemm_tc2_kernel(const __grid_c
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1u;
-          mbar_wait_relaxed(&empty_bar[s], ph ^ 1u);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], stage_bytes);
           const int k0 = kb * BLOCK_K;
           unsigned char* sa = smem_a + (size_t)s * A_STAGE_BYTES;

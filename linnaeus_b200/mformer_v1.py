@@ -41,6 +41,46 @@ class LayerNormChannelsFirst(nn.Module):
         self.eps = eps
 
 
+# bf16 shadow of the parameters for the forward in flight: id(param) -> bf16 view (set by mFormerV1._features)
+_ACTIVE_SHADOW: dict | None = None
+
+
+def _wc(p: torch.Tensor):
+    """Compute-dtype copy of a parameter from the per-step shadow (None in fp32 mode -> the op casts itself)."""
+    return None if _ACTIVE_SHADOW is None else _ACTIVE_SHADOW.get(id(p))
+
+
+class _Bf16Shadow:
+    """bf16 copies of all parameters, refreshed with one cast launch per distinct storage: after FlatAdamW has
+    re-homed the parameters that is two launches per step instead of one per weight."""
+
+    def __init__(self):
+        self.key = None
+        self.bufs = []   # (fp32 storage-wide view, bf16 buffer)
+        self.views = {}
+
+    def refresh(self, params) -> dict:
+        key = tuple(p.data_ptr() for p in params)
+        if key != self.key:
+            by_storage = {}
+            for p in params:
+                st = p.untyped_storage()
+                by_storage.setdefault(st.data_ptr(), (st, []))[1].append(p)
+            self.bufs, self.views = [], {}
+            for _, (st, ps) in by_storage.items():
+                n = st.nbytes() // 4
+                whole = torch.empty(0, dtype=torch.float32, device=ps[0].device).set_(st, 0, (n,))
+                buf = torch.empty(n, dtype=torch.bfloat16, device=ps[0].device)
+                self.bufs.append((whole, buf))
+                for p in ps:
+                    if p.is_contiguous():
+                        self.views[id(p)] = buf[p.storage_offset():p.storage_offset() + p.numel()].view(p.shape)
+            self.key = key
+        for whole, buf in self.bufs:
+            F.cast_bf16(whole, out=buf)
+        return self.views
+
+
 def drop_path_mask(B: int, drop_prob: float, training: bool, device) -> torch.Tensor | None:
     """Per-sample stochastic-depth multiplier floor(keep + U[0,1)) / keep (drop_path.py:11-36); None when inactive.
     The multiplier is applied inside the epilogue of the GEMM that closes the residual branch."""
@@ -68,6 +108,7 @@ class ConvNeXtBlock(nn.Module):
         t = F.layernorm(t.view(-1, C), self.norm.weight, self.norm.bias, 1e-6)
         mask = drop_path_mask(B, self.drop_prob, self.training, x.device)
         return F.mlp2(t, self.pwconv1.weight, self.pwconv1.bias, self.pwconv2.weight, self.pwconv2.bias,
+                      w1c=_wc(self.pwconv1.weight), w2c=_wc(self.pwconv2.weight),
                       act="gelu", residual=x, col_scale=self.gamma, row_scale=mask, rows_per_group=H * W)
 
 
@@ -128,14 +169,15 @@ class RoPE2DMHSABlock(nn.Module):
     def run(self, x: torch.Tensor, H: int, W: int) -> torch.Tensor:
         a = self.attn
         t = F.layernorm(x, self.norm1.weight, self.norm1.bias, 1e-5)
-        qkv = F.linear(t, a.qkv.weight, a.qkv.bias)
+        qkv = F.linear(t, a.qkv.weight, a.qkv.bias, weight_c=_wc(a.qkv.weight))
         o = F.rope_attention(qkv, a.freqs, H, W, a.num_heads, self.extra_token_num)
         B, N = x.shape[0], x.shape[1]
         m1 = drop_path_mask(B, self.drop_prob, self.training, x.device)
-        x = F.linear(o, a.proj.weight, a.proj.bias, residual=x, row_scale=m1, rows_per_group=N)
+        x = F.linear(o, a.proj.weight, a.proj.bias, weight_c=_wc(a.proj.weight), residual=x, row_scale=m1, rows_per_group=N)
         t = F.layernorm(x, self.norm2.weight, self.norm2.bias, 1e-5)
         m2 = drop_path_mask(B, self.drop_prob, self.training, x.device)
-        return F.mlp2(t, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias, act="gelu", residual=x,
+        return F.mlp2(t, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
+                      w1c=_wc(self.mlp.fc1.weight), w2c=_wc(self.mlp.fc2.weight), act="gelu", residual=x,
                       row_scale=m2, rows_per_group=N)
 
 
@@ -157,12 +199,14 @@ def _meta_head(in_dim: int, dim: int) -> nn.Sequential:
 def _run_meta_head(seq: nn.Sequential, meta: torch.Tensor, off: int, dim: int, cdtype: torch.dtype) -> torch.Tensor:
     lin, _, ln, rn = seq[0], seq[1], seq[2], seq[3]
     m = meta[:, off:off + dim]
-    wc = F.compute_copy(lin.weight, cdtype)  # fixes the output dtype of the mixed f32-in GEMM
+    wc = _wc(lin.weight)
+    if wc is None:
+        wc = F.compute_copy(lin.weight, cdtype)  # fixes the output dtype of the mixed f32-in GEMM
     t = F.linear(m, lin.weight, lin.bias, weight_c=wc, act="relu", x_ld=meta.shape[1])
     t = F.layernorm(t, ln.weight, ln.bias, 1e-5)
-    r = F.linear(t, rn.w1.weight, rn.w1.bias, act="relu")
+    r = F.linear(t, rn.w1.weight, rn.w1.bias, weight_c=_wc(rn.w1.weight), act="relu")
     r = F.layernorm(r, rn.norm_fn1.weight, rn.norm_fn1.bias, 1e-5)
-    r = F.linear(r, rn.w2.weight, rn.w2.bias, act="relu")
+    r = F.linear(r, rn.w2.weight, rn.w2.bias, weight_c=_wc(rn.w2.weight), act="relu")
     return F.layernorm(r, rn.norm_fn2.weight, rn.norm_fn2.bias, 1e-5, residual=t)
 
 
@@ -280,6 +324,7 @@ class mFormerV1(nn.Module):
         self.apply(self._init_weights)
         self.dims, self.in_chans = dims, in_chans
         self._compute_dtype: torch.dtype | None = None  # None: follow autocast (on -> bf16, off -> fp32)
+        self._shadow: _Bf16Shadow | None = None
 
     # -- init / metadata properties (mFormerV1.py:351-405) ---------------------
     def _init_weights(self, m):
@@ -347,9 +392,21 @@ class mFormerV1(nn.Module):
         at the reference's batch sizes)."""
         if not x.is_cuda:
             raise RuntimeError("linnaeus_b200.mFormerV1 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        global _ACTIVE_SHADOW
         cd = self._cdtype()  # read before autocast is switched off for the kernels' torch plumbing
-        with torch.autocast("cuda", enabled=False):
-            return self._features(x, meta, cd)
+        prev = _ACTIVE_SHADOW
+        try:
+            with torch.autocast("cuda", enabled=False):
+                if cd == torch.bfloat16:
+                    if self._shadow is None:
+                        self._shadow = _Bf16Shadow()
+                        self._shadow_params = [p for p in self.parameters() if p.ndim >= 2]
+                    _ACTIVE_SHADOW = self._shadow.refresh(self._shadow_params)
+                else:
+                    _ACTIVE_SHADOW = None
+                return self._features(x, meta, cd)
+        finally:
+            _ACTIVE_SHADOW = prev
 
     def _features(self, x, meta, cd):
         B, Cin, Hi, Wi = x.shape
@@ -382,7 +439,8 @@ class mFormerV1(nn.Module):
         cls1, patches = F.tokens_split(x3, n_meta)
         if not self.only_last_cls:
             mlp, ln = self.cl_1_fc[0], self.cl_1_fc[1]
-            c1 = F.mlp2(cls1, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, act="gelu")
+            c1 = F.mlp2(cls1, mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, w1c=_wc(mlp.fc1.weight), w2c=_wc(mlp.fc2.weight),
+                        act="gelu")
             c1 = F.layernorm(c1, ln.weight, ln.bias, 1e-5)
         y = self.downsample_layers[2].run(patches.view(-1, dims[2]), B, H, W)
         H, W = H // 2, W // 2
