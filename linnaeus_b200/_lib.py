@@ -93,11 +93,26 @@ def strerror(code: int) -> str:
     return load().lnx_strerror(code).decode()
 
 
+# LNX_PROFILE=1: every C-ABI call is bracketed by CUDA events on its stream (tools/profile_step.py
+# aggregates them per entry point and shape).  Diagnostic only; never set inside a timed region.
+PROFILE = bool(int(os.environ.get("LNX_PROFILE", "0")))
+profile_log: list = []  # (name, key, start_event, end_event)
+
+
 def call(name: str, *args) -> None:
     """Invoke a C-ABI entry point on the current CUDA stream; raise on a non-zero code."""
     global launch_count
     lib = _lib if _lib is not None else load()
-    code = getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+    if PROFILE:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        code = getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+        e1.record()
+        key = tuple(a for a in args if isinstance(a, (int, bool)) and not isinstance(a, bool) and abs(a) < (1 << 32)) if args else ()
+        profile_log.append((name, key, e0, e1))
+    else:
+        code = getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream)
     launch_count += 1
     if code != 0:
         raise LnxError(f"{name} failed: {strerror(code)} (code {code})")

@@ -3,7 +3,7 @@
 // CTA = one 14x14 output tile x one chunk of channels of one image.  The 20x20
 // input halo tile is staged once in shared memory (16-byte coalesced NHWC loads,
 // zero filled outside the image); a lane owns CPL channels (1 or 2), a warp owns
-// two tile rows, and each thread walks 7-wide output strips so that every value
+// two tile rows, and each thread walks full 14-wide output rows so that every value
 // read from shared memory feeds up to 7 FMAs (the kernel is CUDA-core-FMA bound,
 // not HBM bound: 49 MACs per output element at 4 bytes of traffic).
 #include "lnx_common.cuh"
@@ -14,7 +14,6 @@ namespace {
 
 constexpr int TILE = 14;
 constexpr int HALO = TILE + 6;  // 20
-constexpr int STRIP = 7;
 constexpr int NWARPS = 7;       // warp w -> tile rows 2w, 2w+1
 
 template <typename T, int CPL>
@@ -92,16 +91,17 @@ __global__ void __launch_bounds__(NWARPS * 32) dwconv7_fwd_kernel(const T* __res
 #pragma unroll
   for (int q = 0; q < CPL; ++q) bv[q] = bias ? bias[c0 + cl + q] : 0.f;
 
-#pragma unroll 1
-  for (int s = 0; s < 4; ++s) {  // 2 rows x 2 strips
-    const int orow = warp * 2 + (s >> 1);
-    const int ocol0 = (s & 1) * STRIP;
-    if (h0 + orow >= H || w0 + ocol0 >= W) continue;
-    float acc[STRIP][CPL];
+  // Each thread owns 2 tile rows x 14 columns of its CPL channels.  kh is the outer loop so the 7 taps of a
+  // filter row are fetched once and reused for both output rows: 47 shared loads per 196*CPL FMAs.
+  const int orow0 = warp * 2;
+  if (h0 + orow0 < H) {
+    float acc[2][TILE][CPL];
 #pragma unroll
-    for (int o = 0; o < STRIP; ++o)
+    for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) acc[o][q] = bv[q];
+      for (int o = 0; o < TILE; ++o)
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) acc[rr][o][q] = bv[q];
 #pragma unroll
     for (int kh = 0; kh < 7; ++kh) {
       float wk[7][CPL];
@@ -109,35 +109,42 @@ __global__ void __launch_bounds__(NWARPS * 32) dwconv7_fwd_kernel(const T* __res
       for (int kw = 0; kw < 7; ++kw)
 #pragma unroll
         for (int q = 0; q < CPL; ++q) wk[kw][q] = wsm[(kh * 7 + kw) * CC + cl + q];
-      const T* rowp = tile + ((orow + kh) * HALO + ocol0) * CC + cl;
 #pragma unroll
-      for (int ix = 0; ix < STRIP + 6; ++ix) {
-        float v[CPL];
-        Chan<T, CPL>::ld(rowp + ix * CC, v);
+      for (int rr = 0; rr < 2; ++rr) {
+        const T* rowp = tile + ((orow0 + rr + kh) * HALO) * CC + cl;
 #pragma unroll
-        for (int kw = 0; kw < 7; ++kw) {
-          const int o = ix - kw;
-          if (o >= 0 && o < STRIP) {
+        for (int ix = 0; ix < HALO; ++ix) {
+          float v[CPL];
+          Chan<T, CPL>::ld(rowp + ix * CC, v);
 #pragma unroll
-            for (int q = 0; q < CPL; ++q) acc[o][q] = fmaf(v[q], wk[kw][q], acc[o][q]);
+          for (int kw = 0; kw < 7; ++kw) {
+            const int o = ix - kw;
+            if (o >= 0 && o < TILE) {
+#pragma unroll
+              for (int q = 0; q < CPL; ++q) acc[rr][o][q] = fmaf(v[q], wk[kw][q], acc[rr][o][q]);
+            }
           }
         }
       }
     }
 #pragma unroll
-    for (int o = 0; o < STRIP; ++o) {
-      const int ww = w0 + ocol0 + o;
-      if (ww < W) {
-        T* dst = y + (((long long)b * H + (h0 + orow)) * W + ww) * C + c0 + cl;
-        if (CPL == 2) {
-          if (sizeof(T) == 2) {
-            __nv_bfloat162 p = __floats2bfloat162_rn(acc[o][0], acc[o][CPL - 1]);
-            *reinterpret_cast<__nv_bfloat162*>(dst) = p;
+    for (int rr = 0; rr < 2; ++rr) {
+      const int hh = h0 + orow0 + rr;
+      if (hh >= H) continue;
+#pragma unroll
+      for (int o = 0; o < TILE; ++o) {
+        const int ww = w0 + o;
+        if (ww < W) {
+          T* dst = y + (((long long)b * H + hh) * W + ww) * C + c0 + cl;
+          if constexpr (CPL == 2) {
+            if constexpr (sizeof(T) == 2) {
+              *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(acc[rr][o][0], acc[rr][o][1]);
+            } else {
+              *reinterpret_cast<float2*>(dst) = make_float2(acc[rr][o][0], acc[rr][o][1]);
+            }
           } else {
-            *reinterpret_cast<float2*>(dst) = make_float2(acc[o][0], acc[o][CPL - 1]);
+            dst[0] = from_f32<T>(acc[rr][o][0]);
           }
-        } else {
-          dst[0] = from_f32<T>(acc[o][0]);
         }
       }
     }
@@ -181,28 +188,27 @@ __global__ void __launch_bounds__(NWARPS * 32) dwconv7_wgrad_kernel(const T* __r
     load_tile<T>(gt, dy, b, h0, w0, c0, H, W, C, CC, TILE, TILE, 0, 0);  // zero outside the image
     __syncthreads();
 #pragma unroll 1
-    for (int s = 0; s < 4; ++s) {
-      const int orow = warp * 2 + (s >> 1);
-      const int ocol0 = (s & 1) * STRIP;
-      if (h0 + orow >= H || w0 + ocol0 >= W) continue;
-      float g[STRIP][CPL];
+    for (int rr = 0; rr < 2; ++rr) {  // full 14-wide rows: 20 tile loads feed 98*CPL FMAs per filter row
+      const int orow = warp * 2 + rr;
+      if (h0 + orow >= H) continue;
+      float g[TILE][CPL];
 #pragma unroll
-      for (int o = 0; o < STRIP; ++o) {
-        Chan<T, CPL>::ld(gt + (orow * TILE + ocol0 + o) * CC + cl, g[o]);
+      for (int o = 0; o < TILE; ++o) {
+        Chan<T, CPL>::ld(gt + (orow * TILE + o) * CC + cl, g[o]);
 #pragma unroll
         for (int q = 0; q < CPL; ++q) bacc[q] += g[o][q];
       }
 #pragma unroll
       for (int kh = 0; kh < 7; ++kh) {
-        const T* rowp = tile + ((orow + kh) * HALO + ocol0) * CC + cl;
+        const T* rowp = tile + ((orow + kh) * HALO) * CC + cl;
 #pragma unroll
-        for (int ix = 0; ix < STRIP + 6; ++ix) {
+        for (int ix = 0; ix < HALO; ++ix) {
           float v[CPL];
           Chan<T, CPL>::ld(rowp + ix * CC, v);
 #pragma unroll
           for (int kw = 0; kw < 7; ++kw) {
             const int o = ix - kw;
-            if (o >= 0 && o < STRIP) {
+            if (o >= 0 && o < TILE) {
 #pragma unroll
               for (int q = 0; q < CPL; ++q) wacc[kh * 7 + kw][q] = fmaf(v[q], g[o][q], wacc[kh * 7 + kw][q]);
             }

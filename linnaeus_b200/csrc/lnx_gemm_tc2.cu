@@ -1,18 +1,22 @@
 // Persistent, warp-specialised bf16 GEMM (tcgen05 + TMEM + TMA) with a TMA-fed, TMA-stored epilogue.
 //
-// One CTA per SM walks the output tiles (n fastest).  Roles (64 + 128*G threads, G = 2 or 4 epilogue groups):
+// One CTA per SM walks the output tiles (n fastest).  Roles (64 + 512 threads):
 //   warp 0      TMA producer: A/B k-blocks into a 128B-swizzled smem ring (full/empty mbarriers)
 //   warp 1      MMA issuer: tcgen05.mma cta_group::1, M = 128, N = block_n, accumulators double
 //               buffered in TMEM (2 x 256 columns) so the next tile's MMAs overlap this tile's epilogue
-//   groups      4 warps each (one TMEM lane quarter per warp); group g owns the 64-column blocks
-//               g, g+G, ... of every tile.  Per block: the element-wise input tile (residual or the saved
-//               pre-activation) arrives by TMA (prefetched one block ahead), the accumulator block is read
-//               with four back-to-back tcgen05.ld, bias / GELU / act' / layer-scale / DropPath mask / residual
-//               are applied in registers, results go to a swizzled staging tile and leave with one TMA store
-//               (full 128-byte lines, clipped at the M/N edges by the tensor map).
-// G = 4 when K is small (the HBM-bound conv-stage GEMMs: the epilogue is the whole cost), G = 2 with a deeper
-// operand ring when K is large.  Optional fused column sums of the output (bias gradients) are accumulated per
-// CTA in shared memory across its tiles and flushed with one atomic per column.
+//   warps 2-17  epilogue: 4 groups of 4 warps (a warp may only read its own TMEM lane quarter).  The unit of
+//               work is one [32 rows x 64 columns] block; the 64-column blocks of the CTA's tile sequence are
+//               dealt round-robin to the groups ACROSS tiles, so 3-block tiles (N = 192) still keep all four
+//               groups busy.  Every warp is its own pipeline -- no cross-warp barrier in the epilogue: its
+//               element-wise input block (residual or saved pre-activation) arrives by a per-warp TMA load
+//               prefetched one block ahead, the accumulator is read 32 columns at a time with tcgen05.ld,
+//               bias / GELU / act' / layer scale / DropPath mask / residual are applied in registers, results
+//               go to the warp's private swizzled staging block and leave with one TMA store (full 128-byte
+//               lines, clipped at the M/N edges by the tensor map).
+// The epilogue is compiled per (activation, input kind, aux output, scaling, column sums) so each variant
+// carries only its own instructions: with K = 96 the conv-stage GEMMs are pure epilogue/HBM work.
+// Optional fused column sums of the output (bias gradients) are accumulated per CTA in shared memory across its
+// tiles and flushed with one atomic per column.
 #include "lnx_gemm.cuh"
 #include "lnx_tc_common.cuh"
 
@@ -25,21 +29,21 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int MAX_THREADS = 64 + 128 * 4;
-constexpr int STAGING_BYTES = 16384;  // [128 rows][64 bf16]
+constexpr int MAX_GROUPS = 4;
+constexpr int MAX_EPI_WARPS = 4 * MAX_GROUPS;
+constexpr int MAX_THREADS = 64 + 32 * MAX_EPI_WARPS;
+constexpr int WARP_STAGE_BYTES = 32 * 128;  // [32 rows][64 bf16]
 constexpr int TMEM_STAGE_COLS = 256;
 constexpr int MAX_SMEM = 232448;
 
 struct Tc2Params {
   int M, N, K;
-  int block_n, stages, groups;
+  int block_n, stages;
+  int groups;  // epilogue groups of 4 warps: 4 when the epilogue is the whole cost (small K), 2 with a deeper operand ring
+  int bufs;    // staging blocks per epilogue warp (2: aux output / element-wise input / double-buffered C)
   int a_trans, b_trans;
   int tiles_m, tiles_n;
-  int has_aux;   // second output (pre-activation) staged in buffer B
-  int in_kind;   // 0 none, 1 residual, 2 act_grad_in  -> TMA-loaded into buffer B
 };
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
@@ -47,45 +51,69 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ void pack_store_sw(unsigned char* tile, int r, int j, const float* v) {
-  uint4 raw;
-  __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-  *reinterpret_cast<uint4*>(tile + sw128_chunk(r, j)) = raw;
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
 }
 
-__global__ void __launch_bounds__(MAX_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
-                                                                  const __grid_constant__ CUtensorMap tmIn, const GemmArgs g, const Tc2Params p,
-                                                                  float* __restrict__ colsum_out) {
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8(const uint4& raw, float* u) {
+  u[0] = __uint_as_float(raw.x << 16); u[1] = __uint_as_float(raw.x & 0xffff0000u);
+  u[2] = __uint_as_float(raw.y << 16); u[3] = __uint_as_float(raw.y & 0xffff0000u);
+  u[4] = __uint_as_float(raw.z << 16); u[5] = __uint_as_float(raw.z & 0xffff0000u);
+  u[6] = __uint_as_float(raw.w << 16); u[7] = __uint_as_float(raw.w & 0xffff0000u);
+}
+
+// ACT: LNX_ACT_*.  IN_KIND: 0 none, 1 residual (added last), 2 saved pre-activation (act' multiplies the accumulator).
+// AUX: second output = pre-activation (accumulator + bias).  SCALE: col_scale and/or row_scale.  COLSUM: column sums.
+template <int ACT, int IN_KIND, bool AUX, bool SCALE, bool COLSUM>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmIn, const GemmArgs g, const Tc2Params p,
+                    float* __restrict__ colsum_out) {
+  static_assert(!(AUX && IN_KIND != 0), "the second staging block holds the aux output OR the element-wise input");
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = p.block_n * BLOCK_K * 2;
   unsigned char* smem_a = base;
   unsigned char* smem_b = smem_a + (size_t)p.stages * A_STAGE_BYTES;
-  unsigned char* staging = smem_b + (size_t)p.stages * b_stage_bytes;  // [groups][C tile, B tile][16 KB]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)p.groups * 2 * STAGING_BYTES);
+  unsigned char* staging = smem_b + (size_t)p.stages * b_stage_bytes;  // [epilogue warps][bufs][4 KB]
+  const int EPI_WARPS = 4 * p.groups;
+  const int GROUPS = p.groups;
+  const int NUM_THREADS = blockDim.x;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)EPI_WARPS * p.bufs * WARP_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
-  uint64_t* in_bar = tempty_bar + 2;           // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + 4);
-  float* s_vec = reinterpret_cast<float*>(tmem_slot + 4);   // [4 groups][bias, col_scale][256] of the current tile
-  float* s_colsum = s_vec + 4 * 2 * 256;                    // [N] when colsum_out
+  uint64_t* in_bar = tempty_bar + 2;           // [16]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + MAX_EPI_WARPS);
+  float* s_colsum = reinterpret_cast<float*>(tmem_slot + 4);  // [N] when COLSUM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_tiles = p.tiles_m * p.tiles_n;
-  const int nthreads = blockDim.x;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
-    if (p.has_aux) prefetch_tmap(&tmAux);
-    if (p.in_kind) prefetch_tmap(&tmIn);
+    if (AUX) prefetch_tmap(&tmAux);
+    if (IN_KIND) prefetch_tmap(&tmIn);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -94,11 +122,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gemm_tc2_kernel(const __grid_c
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4 * p.groups);  // one arrival per epilogue warp
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&in_bar[s], 1);
+    for (int s = 0; s < MAX_EPI_WARPS; ++s) mbar_init(&in_bar[s], 1);
     mbar_fence_init();
   }
-  if (colsum_out)
-    for (int i = threadIdx.x; i < p.N; i += nthreads) s_colsum[i] = 0.f;
+  if (COLSUM)
+    for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) s_colsum[i] = 0.f;
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
@@ -115,7 +143,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gemm_tc2_kernel(const __grid_c
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_wait_relaxed(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], stage_bytes);
           const int k0 = kb * BLOCK_K;
           unsigned char* sa = smem_a + (size_t)s * A_STAGE_BYTES;
@@ -147,7 +175,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gemm_tc2_kernel(const __grid_c
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait_relaxed(&full_bar[s], ph);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem_a + (size_t)s * A_STAGE_BYTES);
           const uint32_t sb = smem_u32(smem_b + (size_t)s * b_stage_bytes);
@@ -165,144 +193,174 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) gemm_tc2_kernel(const __grid_c
   } else {
     // ===================== epilogue =====================
     const int e = warp - 2;
-    const int grp = e >> 2;                 // 0 .. groups-1
+    const int grp = e >> 2;                 // 0 .. GROUPS-1
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int r = q * 32 + lane;            // tile row
-    const int gtid = (e & 3) * 32 + lane;   // 0..127 inside the group
-    const int G = p.groups;
-    unsigned char* st_c = staging + (size_t)grp * 2 * STAGING_BYTES;
-    unsigned char* st_b = st_c + STAGING_BYTES;  // aux output OR element-wise input tile
-    float* s_bias = s_vec + grp * 512;
-    float* s_scale = s_bias + 256;
+    unsigned char* st0 = staging + (size_t)e * p.bufs * WARP_STAGE_BYTES;
+    unsigned char* st1 = st0 + WARP_STAGE_BYTES;  // aux output / element-wise input / second C buffer (bufs == 2)
+    const bool dbl = !AUX && !IN_KIND && p.bufs == 2;
+    uint64_t* my_in = &in_bar[e];
     const int n_blocks = (p.block_n + 63) / 64;
-    const bool has_items = grp < n_blocks;
-    uint32_t tl = 0, in_cnt = 0;
+    const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_blocks = my_tiles * n_blocks;
+    uint32_t in_cnt = 0, cbuf = 0;
+    const int r_sw = lane & 7;
 
-    // prefetch the element-wise input tile of this group's first block
-    if (p.in_kind && has_items && gtid == 0 && (int)blockIdx.x < num_tiles) {
-      const int t0 = blockIdx.x;
-      mbar_expect_tx(&in_bar[grp], STAGING_BYTES);
-      tma_load_2d(st_b, &tmIn, &in_bar[grp], (t0 % p.tiles_n) * p.block_n + grp * 64, (t0 / p.tiles_n) * BLOCK_M);
+    // coordinates of this warp's global block index b (deal order: tile-major, then column block)
+    auto block_coords = [&](int b, int& col0, int& row0) {
+      const int tl = b / n_blocks, cb = b - tl * n_blocks;
+      const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+      col0 = (t % p.tiles_n) * p.block_n + cb * 64;
+      row0 = (t / p.tiles_n) * BLOCK_M + q * 32;
+    };
+    if (IN_KIND && lane == 0 && grp < total_blocks) {
+      int c0, r0;
+      block_coords(grp, c0, r0);
+      mbar_expect_tx(my_in, WARP_STAGE_BYTES);
+      tma_load_2d(st1, &tmIn, my_in, c0, r0);
     }
 
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
+    int b = grp;  // next global block of this group
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int t = (int)blockIdx.x + tl * (int)gridDim.x;
       const int m0 = (t / p.tiles_n) * BLOCK_M, n0 = (t % p.tiles_n) * p.block_n;
       const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
-      const int m = m0 + r;
+      const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
-      if (has_items) {
-        // bias / layer-scale of this tile's columns -> shared (read back as broadcasts).  The previous tile's
-        // readers of s_bias/s_scale are past their last named barrier, which precedes this point in program order
-        // for the writers too (same threads).
-        for (int i = gtid; i < p.block_n; i += 128) {
-          const int n = n0 + i;
-          s_bias[i] = (g.bias && n < p.N) ? g.bias[n] : 0.f;
-          s_scale[i] = (g.col_scale && n < p.N) ? g.col_scale[n] : 1.f;
-        }
-      }
-      const float rs = (g.row_scale && row_ok) ? g.row_scale[m / g.rows_per_group] : 1.f;
+      float rs = 1.f;
+      if (SCALE) rs = (g.row_scale && row_ok) ? g.row_scale[m / g.rows_per_group] : 1.f;
       mbar_wait(&tfull_bar[as], aph);
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + as * TMEM_STAGE_COLS + ((uint32_t)(q * 32) << 16);
-      for (int cb = grp; cb < n_blocks; cb += G) {
+      const int b_end = (tl + 1) * n_blocks;
+      for (; b < b_end; b += GROUPS) {
+        const int cb = b - tl * n_blocks;
         const int nb0 = n0 + cb * 64;
         const int ncols = min(64, p.block_n - cb * 64);
-        // the previous TMA store out of this group's staging tiles must have finished reading them
-        if (gtid == 0 && !p.in_kind) tma_store_wait_read();
-        named_bar_sync(1 + grp, 128);
-        // accumulator block -> registers (four loads in flight, one wait)
-        uint32_t acc[64];
+        unsigned char* st_c = (dbl && cbuf) ? st1 : st0;
+        // the TMA store that last read this staging block must be done with it
+        if (lane == 0) {
+          if (dbl) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
         __syncwarp();
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-          if (c4 * 16 < ncols) tmem_ld16_nowait(trow + cb * 64 + c4 * 16, acc + c4 * 16);
-        tmem_ld_wait();
-        if (p.in_kind) {
-          mbar_wait(&in_bar[grp], in_cnt & 1u);
+        if (IN_KIND) {
+          mbar_wait(my_in, in_cnt & 1u);
           ++in_cnt;
         }
+        float csum[2] = {0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j * 8 < ncols) {
-            float vv[8];
-            const int cl = cb * 64 + j * 8;  // column inside the tile
+        for (int half = 0; half < 2; ++half) {
+          if (half * 32 < ncols) {
+            uint32_t acc[32];
+            tmem_ld32_nowait(trow + cb * 64 + half * 32, acc);
+            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(acc[j * 8 + i]) + s_bias[cl + i];
-            if (p.has_aux) pack_store_sw(st_b, r, j, vv);
-            if (p.in_kind == 2) {
-              const uint4 raw = *reinterpret_cast<const uint4*>(st_b + sw128_chunk(r, j));
-              const bf16* u = reinterpret_cast<const bf16*>(&raw);
-              if (g.act == LNX_ACT_GELU) {
+            for (int j = 0; j < 4; ++j) {
+              const int jg = half * 4 + j;
+              const int n = nb0 + jg * 8;
+              const uint32_t soff = (uint32_t)(lane * 128 + ((jg ^ r_sw) << 4));
+              float vv[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] *= gelu_grad_fast(__bfloat162float(u[i]));
-              } else if (g.act == LNX_ACT_RELU) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] = __bfloat162float(u[i]) > 0.f ? vv[i] : 0.f;
+              for (int i = 0; i < 8; ++i) vv[i] = __uint_as_float(acc[j * 8 + i]);
+              if (g.bias && n < p.N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + 1);
+                vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+                vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
               }
-            } else if (g.act == LNX_ACT_GELU) {
+              if (AUX) *reinterpret_cast<uint4*>(st1 + soff) = pack8(vv);
+              if (IN_KIND == 2) {
+                float u[8];
+                unpack8(*reinterpret_cast<const uint4*>(st1 + soff), u);
+                if (ACT == LNX_ACT_GELU) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = gelu_fast(vv[i]);
-            } else if (g.act == LNX_ACT_RELU) {
+                  for (int i = 0; i < 8; ++i) vv[i] *= gelu_grad_tanh3(u[i]);
+                } else if (ACT == LNX_ACT_RELU) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+                  for (int i = 0; i < 8; ++i) vv[i] = u[i] > 0.f ? vv[i] : 0.f;
+                }
+              } else if (ACT == LNX_ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = gelu_tanh3(vv[i]);
+              } else if (ACT == LNX_ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+              }
+              if (SCALE) {
+                if (g.col_scale && n < p.N) {
+                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(g.col_scale + n));
+                  const float4 s1 = __ldg(reinterpret_cast<const float4*>(g.col_scale + n) + 1);
+                  vv[0] *= s0.x * rs; vv[1] *= s0.y * rs; vv[2] *= s0.z * rs; vv[3] *= s0.w * rs;
+                  vv[4] *= s1.x * rs; vv[5] *= s1.y * rs; vv[6] *= s1.z * rs; vv[7] *= s1.w * rs;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) vv[i] *= rs;
+                }
+              }
+              if (IN_KIND == 1) {
+                float u[8];
+                unpack8(*reinterpret_cast<const uint4*>(st1 + soff), u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] += u[i];
+              }
+              if (COLSUM && !row_ok) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = 0.f;  // keeps the fused column sums exact at the M edge
+              }
+              *reinterpret_cast<uint4*>(st_c + soff) = pack8(vv);
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vv[i] *= s_scale[cl + i] * rs;
-            if (p.in_kind == 1) {
-              const uint4 raw = *reinterpret_cast<const uint4*>(st_b + sw128_chunk(r, j));
-              const bf16* u = reinterpret_cast<const bf16*>(&raw);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] += __bfloat162float(u[i]);
-            }
-            if (!row_ok) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vv[i] = 0.f;  // keeps the fused column sums exact at the M edge
-            }
-            pack_store_sw(st_c, r, j, vv);
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1 + grp, 128);
-        if (colsum_out) {
-          // column sums of the bf16 values just staged: thread = (column, half of the rows)
-          const int col = gtid & 63, half = gtid >> 6;
-          if (col < ncols && nb0 + col < p.N) {
-            float a = 0.f;
-            const int j = col >> 3, e2 = col & 7;
+        __syncwarp();
+        if (COLSUM) {
+          // column sums of the bf16 values just staged: lane = column pair (2 lane, 2 lane + 1) over this warp's 32 rows
+          const int jg = lane >> 2;
 #pragma unroll 8
-            for (int rr = half * 64; rr < half * 64 + 64; ++rr)
-              a += __bfloat162float(*reinterpret_cast<const bf16*>(st_c + sw128_chunk(rr, j) + e2 * 2));
-            atomicAdd(&s_colsum[nb0 + col], a);
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(st_c + rr * 128 + ((jg ^ (rr & 7)) << 4) + (lane & 3) * 4);
+            csum[0] += __uint_as_float(w << 16);
+            csum[1] += __uint_as_float(w & 0xffff0000u);
           }
+          const int c = nb0 + 2 * lane;
+          if (2 * lane < ncols && c < p.N) {
+            atomicAdd(&s_colsum[c], csum[0]);
+            atomicAdd(&s_colsum[c + 1], csum[1]);
+          }
+          __syncwarp();
         }
-        if (gtid == 0) {
-          tma_store_2d(&tmC, st_c, nb0, m0);
-          if (p.has_aux) tma_store_2d(&tmAux, st_b, nb0, m0);
+        if (lane == 0) {
+          const int row0 = m0 + q * 32;
+          if (row0 < p.M) {
+            tma_store_2d(&tmC, st_c, nb0, row0);
+            if (AUX) tma_store_2d(&tmAux, st1, nb0, row0);
+          }
           tma_store_commit();
-          if (p.in_kind) {
-            // every thread of the group has consumed st_b (barrier above): prefetch the next block's input tile
-            int nt = t, ncb = cb + G;
-            if (ncb >= n_blocks) { nt = t + gridDim.x; ncb = grp; }
-            if (nt < num_tiles) {
-              mbar_expect_tx(&in_bar[grp], STAGING_BYTES);
-              tma_load_2d(st_b, &tmIn, &in_bar[grp], (nt % p.tiles_n) * p.block_n + ncb * 64, (nt / p.tiles_n) * BLOCK_M);
+          if (IN_KIND) {
+            // every lane has consumed st1 (syncwarp above): prefetch this warp's next input block
+            const int nb = b + GROUPS;
+            if (nb < total_blocks) {
+              int c0, r0;
+              block_coords(nb, c0, r0);
+              mbar_expect_tx(my_in, WARP_STAGE_BYTES);
+              tma_load_2d(st1, &tmIn, my_in, c0, r0);
             }
-            tma_store_wait_read();  // st_c is free again before the group passes the next block's first barrier
           }
         }
+        cbuf ^= 1u;
       }
-      // this warp is done reading the accumulator
+      // this warp is done reading the accumulator of tile tl
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
-    if (gtid == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (colsum_out)
-    for (int i = threadIdx.x; i < p.N; i += nthreads) {
+  if (COLSUM)
+    for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) {
       const float v = s_colsum[i];
       if (v != 0.f) atomicAdd(colsum_out + i, v);
     }
@@ -334,62 +392,116 @@ int pick_block_n2(int N, bool b_trans) {
   return 256;
 }
 
+struct Launch {
+  CUtensorMap tmA, tmB, tmC, tmAux, tmIn;
+  GemmArgs g;
+  Tc2Params p;
+  float* colsum_out;
+  int grid;
+  size_t smem;
+  cudaStream_t st;
+};
+
+template <int ACT, int IN_KIND, bool AUX, bool SCALE, bool COLSUM>
+int launch_variant(const Launch& L) {
+  auto kern = gemm_tc2_kernel<ACT, IN_KIND, AUX, SCALE, COLSUM>;
+  static int smem_set = 0;
+  if ((int)L.smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) return lnx_set_cuda_error(e);
+    smem_set = (int)L.smem;
+  }
+  kern<<<L.grid, 64 + 128 * L.p.groups, L.smem, L.st>>>(L.tmA, L.tmB, L.tmC, L.tmAux, L.tmIn, L.g, L.p, L.colsum_out);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+template <int ACT>
+int launch_act(const Launch& L, int in_kind, bool aux, bool scale, bool colsum) {
+  if (in_kind == 2) {
+    if (aux || scale) return LNX_ERR_UNSUPPORTED;
+    return colsum ? launch_variant<ACT, 2, false, false, true>(L) : launch_variant<ACT, 2, false, false, false>(L);
+  }
+  if (colsum || scale || in_kind) return LNX_ERR_UNSUPPORTED;
+  return aux ? launch_variant<ACT, 0, true, false, false>(L) : launch_variant<ACT, 0, false, false, false>(L);
+}
+
+int launch_none(const Launch& L, int in_kind, bool aux, bool scale, bool colsum) {
+  if (in_kind == 2 || aux) return LNX_ERR_UNSUPPORTED;  // act' of "none" is the identity: callers never pass it
+  if (colsum) {
+    if (in_kind || scale) return LNX_ERR_UNSUPPORTED;
+    return launch_variant<LNX_ACT_NONE, 0, false, false, true>(L);
+  }
+  if (in_kind == 1) return scale ? launch_variant<LNX_ACT_NONE, 1, false, true, false>(L) : launch_variant<LNX_ACT_NONE, 1, false, false, false>(L);
+  return scale ? launch_variant<LNX_ACT_NONE, 0, false, true, false>(L) : launch_variant<LNX_ACT_NONE, 0, false, false, false>(L);
+}
+
 }  // namespace
 
 // bf16 in / bf16 out, no split-K.  colsum_out (nullable, float[N], +=) receives the column sums of C.
 int lnx_gemm_tc2(const GemmArgs& g, float* colsum_out, cudaStream_t st) {
   if (g.N % 8 != 0 || g.lda % 8 != 0 || g.ldb % 8 != 0 || g.accumulate) return LNX_ERR_UNSUPPORTED;
   if (!lnx_aligned16(g.A) || !lnx_aligned16(g.B) || !lnx_aligned16(g.C) || !lnx_aligned16(g.aux_out) || !lnx_aligned16(g.act_grad_in) ||
-      !lnx_aligned16(g.residual))
+      !lnx_aligned16(g.residual) || !lnx_aligned16(g.bias) || !lnx_aligned16(g.col_scale))
     return LNX_ERR_UNSUPPORTED;
   if (colsum_out && g.N > 4096) return LNX_ERR_UNSUPPORTED;
-  // buffer B of a group holds the aux output OR one element-wise input tile
+  // the second staging block of a warp holds the aux output OR one element-wise input block
   const int n_b_users = (g.aux_out ? 1 : 0) + (g.act_grad_in ? 1 : 0) + (g.residual ? 1 : 0);
   if (n_b_users > 1) return LNX_ERR_UNSUPPORTED;
-  Tc2Params p;
+  Launch L;
+  Tc2Params& p = L.p;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.a_trans = g.a_trans; p.b_trans = g.b_trans;
   p.block_n = pick_block_n2(g.N, g.b_trans != 0);
   p.tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (g.N + p.block_n - 1) / p.block_n;
-  p.has_aux = g.aux_out ? 1 : 0;
-  p.in_kind = g.residual ? 1 : (g.act_grad_in ? 2 : 0);
+  const int in_kind = g.residual ? 1 : (g.act_grad_in ? 2 : 0);
   const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
   const int num_kb = (g.K + BLOCK_K - 1) / BLOCK_K;
-  const int n_blocks = (p.block_n + 63) / 64;
-  // small K: the epilogue is the whole cost -> 4 groups; large K: deeper operand ring, 2 groups
-  p.groups = (num_kb <= 4 && n_blocks >= 3) ? 4 : 2;
-  auto fixed_bytes = [&](int groups) { return 1024 + groups * 2 * STAGING_BYTES + 512 + 4 * 2 * 256 * 4 + (colsum_out ? g.N * 4 : 0); };
-  int stages = (MAX_SMEM - fixed_bytes(p.groups)) / stage_bytes;
-  if (stages < 2 && p.groups == 4) {
+  // small K: the epilogue is the whole cost -> 4 groups, double staging; large K: deeper operand ring first
+  auto fixed_bytes = [&](int groups, int bufs) { return 1024 + 4 * groups * bufs * WARP_STAGE_BYTES + 512 + (colsum_out ? g.N * 4 : 0); };
+  const int want = min(4, 2 * num_kb);
+  p.groups = num_kb <= 4 ? 4 : 2;
+  p.bufs = 2;
+  int stages = (MAX_SMEM - fixed_bytes(p.groups, p.bufs)) / stage_bytes;
+  if (stages < want && n_b_users == 0) {
+    p.bufs = 1;
+    stages = (MAX_SMEM - fixed_bytes(p.groups, p.bufs)) / stage_bytes;
+  }
+  if (stages < want && p.groups == 4) {
     p.groups = 2;
-    stages = (MAX_SMEM - fixed_bytes(p.groups)) / stage_bytes;
+    p.bufs = 2;
+    stages = (MAX_SMEM - fixed_bytes(p.groups, p.bufs)) / stage_bytes;
+    if (stages < want && n_b_users == 0) {
+      p.bufs = 1;
+      stages = (MAX_SMEM - fixed_bytes(p.groups, p.bufs)) / stage_bytes;
+    }
   }
   if (stages < 2) return LNX_ERR_UNSUPPORTED;
-  p.stages = min(min(stages, 6), max(2, 2 * num_kb));
-  const size_t smem = (size_t)p.stages * stage_bytes + fixed_bytes(p.groups);
+  p.stages = min(min(stages, 8), max(2, 2 * num_kb));
+  L.smem = (size_t)p.stages * stage_bytes + fixed_bytes(p.groups, p.bufs);
 
-  CUtensorMap tmA, tmB, tmC, tmAux, tmIn;
   bool ok;
-  if (!g.a_trans) ok = tmap2d(&tmA, g.A, g.K, g.M, g.lda, BLOCK_M);
-  else ok = tmap2d(&tmA, g.A, g.M, g.K, g.lda, 64);
-  if (!g.b_trans) ok = ok && tmap2d(&tmB, g.B, g.K, g.N, g.ldb, p.block_n);
-  else ok = ok && tmap2d(&tmB, g.B, g.N, g.K, g.ldb, 64);
-  ok = ok && tmap2d(&tmC, g.C, g.N, g.M, g.N, BLOCK_M);
-  if (g.aux_out) ok = ok && tmap2d(&tmAux, g.aux_out, g.N, g.M, g.N, BLOCK_M);
-  else tmAux = tmC;
-  if (p.in_kind) ok = ok && tmap2d(&tmIn, p.in_kind == 1 ? g.residual : g.act_grad_in, g.N, g.M, g.N, BLOCK_M);
-  else tmIn = tmC;
+  if (!g.a_trans) ok = tmap2d(&L.tmA, g.A, g.K, g.M, g.lda, BLOCK_M);
+  else ok = tmap2d(&L.tmA, g.A, g.M, g.K, g.lda, 64);
+  if (!g.b_trans) ok = ok && tmap2d(&L.tmB, g.B, g.K, g.N, g.ldb, p.block_n);
+  else ok = ok && tmap2d(&L.tmB, g.B, g.N, g.K, g.ldb, 64);
+  ok = ok && tmap2d(&L.tmC, g.C, g.N, g.M, g.N, 32);
+  if (g.aux_out) ok = ok && tmap2d(&L.tmAux, g.aux_out, g.N, g.M, g.N, 32);
+  else L.tmAux = L.tmC;
+  if (in_kind) ok = ok && tmap2d(&L.tmIn, in_kind == 1 ? g.residual : g.act_grad_in, g.N, g.M, g.N, 32);
+  else L.tmIn = L.tmC;
   if (!ok) return LNX_ERR_UNSUPPORTED;
 
-  static int smem_set = 0;
-  if ((int)smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return lnx_set_cuda_error(e);
-    smem_set = (int)smem;
+  L.g = g;
+  L.colsum_out = colsum_out;
+  L.grid = min(p.tiles_m * p.tiles_n, kNumSMs);
+  L.st = st;
+  const bool aux = g.aux_out != nullptr, scale = g.col_scale || g.row_scale, colsum = colsum_out != nullptr;
+  switch (g.act) {
+    case LNX_ACT_NONE: return launch_none(L, in_kind, aux, scale, colsum);
+    case LNX_ACT_GELU: return launch_act<LNX_ACT_GELU>(L, in_kind, aux, scale, colsum);
+    case LNX_ACT_RELU: return launch_act<LNX_ACT_RELU>(L, in_kind, aux, scale, colsum);
   }
-  const int grid = min(p.tiles_m * p.tiles_n, kNumSMs);
-  gemm_tc2_kernel<<<grid, 64 + 128 * p.groups, smem, st>>>(tmA, tmB, tmC, tmAux, tmIn, g, p, colsum_out);
-  LNX_CHECK_LAUNCH();
-  return LNX_OK;
+  return LNX_ERR_UNSUPPORTED;
 }

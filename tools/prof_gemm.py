@@ -40,3 +40,33 @@ bytes_ = [(M*K + 2*M*N)*2, (M*N + 2*M*K)*2, (M*K + 2*M*N)*2, (M*N + M*K)*2, (M*N
 for i, n in enumerate(names):
     ms = ev[i].elapsed_time(ev[i+1])
     print(f"{n:8s} {ms:7.3f} ms  {bytes_[i]/ms/1e6:7.0f} GB/s")
+
+# ---- transformer-stage shapes (tensor-bound): report TFLOP/s
+def bench(name, fn, flops, n=5):
+    for _ in range(2):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"{name:28s} {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s")
+
+for (M2, D) in ((B * 200, 384), (B * 53, 768)):
+    x = torch.randn(M2, D, device=dev).bfloat16()
+    wq = (torch.randn(3 * D, D, device=dev) / 20).bfloat16()
+    w1 = (torch.randn(4 * D, D, device=dev) / 20).bfloat16()
+    w2_ = (torch.randn(D, 4 * D, device=dev) / 20).bfloat16()
+    bq = torch.randn(3 * D, device=dev); b1 = torch.randn(4 * D, device=dev); b2 = torch.randn(D, device=dev)
+    oq = torch.empty(M2, 3 * D, device=dev, dtype=torch.bfloat16)
+    h = torch.empty(M2, 4 * D, device=dev, dtype=torch.bfloat16); pre = torch.empty_like(h); dpre2 = torch.empty_like(h)
+    y2 = torch.empty(M2, D, device=dev, dtype=torch.bfloat16)
+    cs2 = torch.zeros(4 * D, device=dev)
+    bench(f"qkv  {M2}x{3*D}x{D}", lambda: F.gemm(x, wq, M2, 3 * D, D, out=oq, bias=bq), 2 * M2 * 3 * D * D)
+    bench(f"fc1  {M2}x{4*D}x{D} gelu+aux", lambda: F.gemm(x, w1, M2, 4 * D, D, out=h, bias=b1, act=1, aux_out=pre), 2 * M2 * 4 * D * D)
+    bench(f"fc2  {M2}x{D}x{4*D} +res", lambda: F.gemm(h, w2_, M2, D, 4 * D, out=y2, bias=b2, residual=x), 2 * M2 * 4 * D * D)
+    bench(f"dpre {M2}x{4*D}x{D} act'", lambda: F.gemm(y2, w2_, M2, 4 * D, D, b_trans=True, ldb=4 * D, out=dpre2, act=1, act_grad_in=pre, colsum_out=cs2), 2 * M2 * 4 * D * D)
+    bench(f"dx   {M2}x{D}x{4*D}", lambda: F.gemm(dpre2, w1, M2, D, 4 * D, b_trans=True, ldb=D, out=y2), 2 * M2 * 4 * D * D)
+    bench(f"dw1  {4*D}x{D}x{M2}", lambda: F.wgrad(dpre2, x), 2 * M2 * 4 * D * D)
