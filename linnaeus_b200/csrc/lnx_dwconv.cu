@@ -263,6 +263,10 @@ int wgrad_launch(const void* x, const void* dy, float* dw, float* db, int B, int
 
 }  // namespace
 
+// bf16: packed-fp32x2 (FFMA2) kernels of lnx_dwconv_bf16.cu
+int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, cudaStream_t st);
+int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, cudaStream_t st);
+
 extern "C" int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, int dtype, lnx_stream_t s) {
   LNX_REQUIRE(x && w49c && y, LNX_ERR_NULL);
   LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0, LNX_ERR_SHAPE);
@@ -270,7 +274,7 @@ extern "C" int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bi
   cudaStream_t st = (cudaStream_t)s;
   const bool pair = (C % 64 == 0);
   if (dtype == LNX_F32) return pair ? fwd_launch<float, 2>(x, w49c, bias, y, B, H, W, C, st) : fwd_launch<float, 1>(x, w49c, bias, y, B, H, W, C, st);
-  if (dtype == LNX_BF16) return pair ? fwd_launch<bf16, 2>(x, w49c, bias, y, B, H, W, C, st) : fwd_launch<bf16, 1>(x, w49c, bias, y, B, H, W, C, st);
+  if (dtype == LNX_BF16) return lnx_dwconv7_fwd_bf16(x, w49c, bias, y, B, H, W, C, st);
   return LNX_ERR_DTYPE;
 }
 
@@ -281,6 +285,6 @@ extern "C" int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, fl
   cudaStream_t st = (cudaStream_t)s;
   const bool pair = (C % 64 == 0);
   if (dtype == LNX_F32) return pair ? wgrad_launch<float, 2>(x, dy, dw49c, dbias, B, H, W, C, st) : wgrad_launch<float, 1>(x, dy, dw49c, dbias, B, H, W, C, st);
-  if (dtype == LNX_BF16) return pair ? wgrad_launch<bf16, 2>(x, dy, dw49c, dbias, B, H, W, C, st) : wgrad_launch<bf16, 1>(x, dy, dw49c, dbias, B, H, W, C, st);
+  if (dtype == LNX_BF16) return lnx_dwconv7_wgrad_bf16(x, dy, dw49c, dbias, B, H, W, C, st);
   return LNX_ERR_DTYPE;
 }

@@ -1,0 +1,282 @@
+// Depthwise 7x7 (pad 3, stride 1) on NHWC bf16 with packed fp32x2 FMAs (FFMA2, sm_100): forward / data
+// gradient and weight gradient.
+//
+// The op is bound by the fp32 FMA pipe (49 MACs per output element against 4 bytes of traffic), and on
+// Blackwell the 3-register scalar FFMA issues at half rate: the full rate needs fma.rn.f32x2.  So a lane owns a
+// channel PAIR (one 32-bit shared load = both channels of one pixel, one FFMA2 = both channels of one tap) and
+// keeps fp32x2 accumulators for a strip of 7 outputs per row, so every loaded pixel feeds up to 7 FFMA2.
+// A warp = 16 channel pairs x two half strips (columns 0-6 / 7-13 of a tile row); the two 64-byte segments a
+// warp reads are 7 pixels = 448 bytes apart, i.e. on disjoint shared-memory banks.
+//
+// Work item = one 14x14 output tile of one image x one 32-channel chunk.  CTAs are persistent per channel chunk
+// and double buffered: one thread issues the TMA load (4-D tensor map over [B][H][W][C]; negative / overhanging
+// coordinates are zero filled by the hardware = the conv padding) of the NEXT 20x20 halo tile while all warps
+// compute the current one, so no instruction is spent on staging.  The weight-gradient kernel keeps 49 fp32x2
+// partial sums per lane in registers across all tiles the CTA visits.
+#include "lnx_common.cuh"
+#include "lnx_tc_common.cuh"
+
+using namespace lnx;
+using namespace lnx_tc;
+
+namespace {
+
+constexpr int TILE = 14;
+constexpr int HALO = TILE + 6;  // 20
+constexpr int NWARPS = 7;       // warp w -> tile rows 2w, 2w+1
+constexpr int NTHREADS = NWARPS * 32;
+constexpr int PW = 16;          // channel pairs per pixel of a chunk
+constexpr int CC = 2 * PW;      // 32 channels per chunk
+constexpr int HALO_BYTES = HALO * HALO * CC * 2;  // 25600
+constexpr int CENTER_BYTES = TILE * TILE * CC * 2;  // 12544
+constexpr int CENTER_PAD = 12800;                   // keeps every buffer 256-byte aligned
+
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+struct TileCoord {
+  int b, h0, w0;
+};
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_w, int tiles_h) {
+  TileCoord c;
+  const int tw = t % tiles_w;
+  t /= tiles_w;
+  c.w0 = tw * TILE;
+  c.h0 = (t % tiles_h) * TILE;
+  c.b = t / tiles_h;
+  return c;
+}
+
+// ------------------------------------------------------------------ forward (and data gradient with flipped taps)
+__global__ void __launch_bounds__(NTHREADS, 3)
+    dwconv7_fwd_x2_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w49c, const float* __restrict__ bias,
+                          bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = smem_raw;                                              // [2][20][20][CC] bf16
+  float2* wsm = reinterpret_cast<float2*>(smem_raw + 2 * HALO_BYTES);           // [49][PW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * HALO_BYTES + 49 * CC * 4);  // [2]
+
+  const int c0 = blockIdx.y * CC;
+  const int total = B * tiles_h * tiles_w;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) reinterpret_cast<float*>(wsm)[i] = w49c[(i / CC) * C + c0 + (i % CC)];
+  __syncthreads();
+  if (threadIdx.x == 0 && (int)blockIdx.x < total) {
+    const TileCoord tc = tile_coord(blockIdx.x, tiles_w, tiles_h);
+    mbar_expect_tx(&full[0], HALO_BYTES);
+    tma_load_4d(tiles, &tmX, &full[0], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
+  }
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = lane & (PW - 1);
+  const int col0 = (lane >> 4) * 7;
+  const int orow0 = warp * 2;
+  float2 bv = make_float2(0.f, 0.f);
+  if (bias) bv = *reinterpret_cast<const float2*>(bias + c0 + 2 * p);
+
+  int it = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int tn = t + gridDim.x;
+    if (threadIdx.x == 0 && tn < total) {  // buffer buf^1 was released by the barrier that ended the previous iteration
+      const TileCoord tc = tile_coord(tn, tiles_w, tiles_h);
+      mbar_expect_tx(&full[buf ^ 1], HALO_BYTES);
+      tma_load_4d(tiles + (buf ^ 1) * HALO_BYTES, &tmX, &full[buf ^ 1], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
+    }
+    const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
+    mbar_wait(&full[buf], (it >> 1) & 1);
+
+    if (tc.h0 + orow0 < H) {
+      float2 acc[2][7];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int o = 0; o < 7; ++o) acc[rr][o] = bv;
+      const uint32_t* tp = reinterpret_cast<const uint32_t*>(tiles + buf * HALO_BYTES) + ((orow0 * HALO + col0) * PW + p);
+#pragma unroll
+      for (int kh = 0; kh < 7; ++kh) {
+        float2 wk[7];
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) wk[kw] = wsm[(kh * 7 + kw) * PW + p];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const uint32_t* rowp = tp + (rr + kh) * HALO * PW;
+#pragma unroll
+          for (int ix = 0; ix < 13; ++ix) {
+            const float2 v = unpack_bf16x2(rowp[ix * PW]);
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+              const int o = ix - kw;
+              if (o >= 0 && o < 7) acc[rr][o] = ffma2(v, wk[kw], acc[rr][o]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int hh = tc.h0 + orow0 + rr;
+        if (hh < H) {
+          bf16* yrow = y + (((long long)tc.b * H + hh) * W + tc.w0 + col0) * C + c0 + 2 * p;
+#pragma unroll
+          for (int o = 0; o < 7; ++o)
+            if (tc.w0 + col0 + o < W)
+              *reinterpret_cast<__nv_bfloat162*>(yrow + (long long)o * C) = __floats2bfloat162_rn(acc[rr][o].x, acc[rr][o].y);
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with tiles[buf]: it may be refilled by the next iteration's TMA
+  }
+}
+
+// ------------------------------------------------------------------ weight gradient
+__global__ void __launch_bounds__(NTHREADS, 2)
+    dwconv7_wgrad_x2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, float* __restrict__ dw49c,
+                            float* __restrict__ dbias, int B, int H, int W, int C, int tiles_w, int tiles_h) {
+  constexpr int STAGE = HALO_BYTES + CENTER_PAD;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* stages = smem_raw;                                        // [2]{x halo [20][20][CC], dy [14][14][CC]}
+  float* red = reinterpret_cast<float*>(smem_raw + 2 * STAGE);             // [50][CC]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * STAGE + 50 * CC * 4);
+
+  const int c0 = blockIdx.y * CC;
+  const int total = B * tiles_h * tiles_w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = lane & (PW - 1);
+  const int col0 = (lane >> 4) * 7;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmG);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 50 * CC; i += NTHREADS) red[i] = 0.f;
+  __syncthreads();
+  auto issue = [&](int t, int buf) {
+    const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
+    unsigned char* st = stages + buf * STAGE;
+    mbar_expect_tx(&full[buf], HALO_BYTES + CENTER_BYTES);
+    tma_load_4d(st, &tmX, &full[buf], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
+    tma_load_4d(st + HALO_BYTES, &tmG, &full[buf], c0, tc.w0, tc.h0, tc.b);
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
+
+  float2 wacc[49];
+  float2 bacc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 49; ++k) wacc[k] = make_float2(0.f, 0.f);
+
+  int it = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (threadIdx.x == 0 && t + (int)gridDim.x < total) issue(t + gridDim.x, buf ^ 1);
+    mbar_wait(&full[buf], (it >> 1) & 1);
+    const unsigned char* st = stages + buf * STAGE;
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {  // strips of 7 outputs: 13 tile loads feed 49 FFMA2 per filter row
+      const int orow = warp * 2 + rr;
+      float2 g[7];
+      const uint32_t* gp = reinterpret_cast<const uint32_t*>(st + HALO_BYTES) + ((orow * TILE + col0) * PW + p);
+#pragma unroll
+      for (int o = 0; o < 7; ++o) {
+        g[o] = unpack_bf16x2(gp[o * PW]);  // rows / columns beyond the image were zero filled
+        bacc.x += g[o].x;
+        bacc.y += g[o].y;
+      }
+      const uint32_t* tp = reinterpret_cast<const uint32_t*>(st) + ((orow * HALO + col0) * PW + p);
+#pragma unroll
+      for (int kh = 0; kh < 7; ++kh) {
+        const uint32_t* rowp = tp + kh * HALO * PW;
+#pragma unroll
+        for (int ix = 0; ix < 13; ++ix) {
+          const float2 v = unpack_bf16x2(rowp[ix * PW]);
+#pragma unroll
+          for (int kw = 0; kw < 7; ++kw) {
+            const int o = ix - kw;
+            if (o >= 0 && o < 7) wacc[kh * 7 + kw] = ffma2(v, g[o], wacc[kh * 7 + kw]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 49; ++k) {
+    atomicAdd(&red[k * CC + 2 * p], wacc[k].x);
+    atomicAdd(&red[k * CC + 2 * p + 1], wacc[k].y);
+  }
+  atomicAdd(&red[49 * CC + 2 * p], bacc.x);
+  atomicAdd(&red[49 * CC + 2 * p + 1], bacc.y);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) atomicAdd(dw49c + (i / CC) * C + c0 + (i % CC), red[i]);
+  if (dbias)
+    for (int i = threadIdx.x; i < CC; i += NTHREADS) atomicAdd(dbias + c0 + i, red[49 * CC + i]);
+}
+
+// [B][H][W][C] bf16, box = (CC channels, bw, bh, 1 image), no swizzle, zero fill outside
+bool make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int bw, int bh) {
+  auto enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)CC, (cuuint32_t)bw, (cuuint32_t)bh, 1u};
+  cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, cudaStream_t st) {
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 7u)) return LNX_ERR_ALIGN;
+  if (C % CC != 0) return LNX_ERR_SHAPE;
+  CUtensorMap tmX;
+  if (!make_nhwc_tmap(&tmX, x, B, H, W, C, HALO, HALO)) return LNX_ERR_UNSUPPORTED;
+  const int tiles_w = (W + TILE - 1) / TILE, tiles_h = (H + TILE - 1) / TILE;
+  const size_t smem = 2 * HALO_BYTES + 49 * CC * 4 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv7_fwd_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return lnx_set_cuda_error(e);
+    attr_set = true;
+  }
+  const int chunks = C / CC;
+  const int total = B * tiles_h * tiles_w;
+  const int gx = max(1, min(total, (kNumSMs * 3 + chunks - 1) / chunks));
+  dwconv7_fwd_x2_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, cudaStream_t st) {
+  if (C % CC != 0) return LNX_ERR_SHAPE;
+  CUtensorMap tmX, tmG;
+  if (!make_nhwc_tmap(&tmX, x, B, H, W, C, HALO, HALO) || !make_nhwc_tmap(&tmG, dy, B, H, W, C, TILE, TILE)) return LNX_ERR_UNSUPPORTED;
+  const int tiles_w = (W + TILE - 1) / TILE, tiles_h = (H + TILE - 1) / TILE;
+  const size_t smem = 2 * (HALO_BYTES + CENTER_PAD) + 50 * CC * 4 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv7_wgrad_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return lnx_set_cuda_error(e);
+    attr_set = true;
+  }
+  const int chunks = C / CC;
+  const int total = B * tiles_h * tiles_w;
+  const int gx = max(1, min(total, (kNumSMs * 2 + chunks - 1) / chunks));
+  dwconv7_wgrad_x2_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, tmG, dw49c, dbias, B, H, W, C, tiles_w, tiles_h);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
