@@ -40,14 +40,18 @@ for (H, C) in ((56, 96), (28, 192)):
     bench(f"dwconv7 wgrad {H}x{H}x{C}", lambda: call("lnx_dwconv7_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H, H, C, dt(x)), 2 * nb, flops=fma)
 
 for (rows, C) in ((B * 3136, 96), (B * 784, 192), (B * 200, 384), (B * 53, 768)):
-    x = torch.randn(rows, C, device=dev).bfloat16().requires_grad_(True)
-    w = torch.randn(C, device=dev, requires_grad=True)
-    b = torch.randn(C, device=dev, requires_grad=True)
-    y = F.layernorm(x, w, b, 1e-6)
-    g = torch.randn_like(y)
+    x = torch.randn(rows, C, device=dev).bfloat16()
+    g = torch.randn_like(x)
+    res = torch.randn_like(x)
+    y = torch.empty_like(x)
+    dx = torch.empty_like(x)
+    w = torch.randn(C, device=dev)
+    b = torch.randn(C, device=dev)
+    mean = torch.empty(rows, device=dev)
+    rstd = torch.empty(rows, device=dev)
+    dw = torch.zeros(C, device=dev)
+    db = torch.zeros(C, device=dev)
     nb = rows * C * 2
-    with torch.no_grad():
-        bench(f"layernorm fwd {rows}x{C}", lambda: F.layernorm(x, w, b, 1e-6), 2 * nb)
-    def bwd():
-        y.backward(g, retain_graph=True)
-    bench(f"layernorm bwd {rows}x{C}", bwd, 3 * nb)
+    bench(f"layernorm fwd {rows}x{C}", lambda: call("lnx_layernorm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), None, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C, 1e-6, dt(x)), 2 * nb)
+    bench(f"layernorm fwd+res {rows}x{C}", lambda: call("lnx_layernorm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), res.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C, 1e-6, dt(x)), 3 * nb)
+    bench(f"layernorm bwd {rows}x{C}", lambda: call("lnx_layernorm_bwd", g.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, C, dt(x)), 3 * nb)

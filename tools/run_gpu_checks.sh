@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 rc=0
 for f in "$@"; do
   name=$(basename "$f" .py)
-  timeout 900 python -m pytest "$f" -q -m gpu --no-header -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1
+  timeout 420 python -m pytest "$f" -q -m gpu --no-header -p no:cacheprovider --timeout 120 > "gpurun_out/${name}.log" 2>&1
   r=$?
   echo "== $f exit $r"
   tail -n 25 "gpurun_out/${name}.log"
