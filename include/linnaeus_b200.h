@@ -93,6 +93,14 @@ int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, void* y
 int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, int dtype, lnx_stream_t s);
 
 /* ---- GEMM with fused epilogue ------------------------------------------ */
+/* Weight (+ bias) gradient of y = x W^T + b on the tensor cores, reduction over the M rows (tokens):
+ *   dw[N,K] += dy[M,N]^T x[M,K],   db[N] += sum_m dy[m,:]   (db may be NULL).
+ * dy / x are bf16 row-major with pitches ldy / ldx (elements); split-K over all SMs, db from an extra
+ * N = 16 MMA against a tile of ones.  Replaces autograd's Linear weight/bias backward
+ * (torch.nn.functional.linear backward; R/models/blocks/{convnext.py:79-86, mlp.py:61-65, rope_2d_mhsa.py:292-294}). */
+int lnx_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx, float* dw, float* db, int64_t M, int N, int K, int dtype,
+              lnx_stream_t s);
+
 /* acc[m,n] = sum_k A(m,k) * B(n,k)
  *   a_trans = 0: A stored [M,K] (row pitch lda); 1: stored [K,M]
  *   b_trans = 0: B stored [N,K] (row pitch ldb); 1: stored [K,N]

@@ -39,6 +39,7 @@ SIGNATURES = {
     "lnx_dwconv7_fwd": [P, P, P, P, I, I, I, I, I, P],
     "lnx_dwconv7_wgrad": [P, P, P, P, I, I, I, I, I, P],
     "lnx_gemm": [I, P, L, I, P, L, I, P, I, I, I, I, P, I, P, P, P, P, P, I, P, I, I, P],
+    "lnx_wgrad": [P, L, P, L, P, P, L, I, I, I, P],
     "lnx_rowscale": [P, P, P, L, I, I, I, P],
     "lnx_rope_table": [P, P, P, I, I, I, I, P],
     "lnx_rope_qk_fwd": [P, P, P, P, P, I, I, I, I, I, F, I, P],

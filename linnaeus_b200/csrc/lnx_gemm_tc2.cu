@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
-  uint64_t* in_bar = tempty_bar + 2;           // [16]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + MAX_EPI_WARPS);
+  uint64_t* in_bar = tempty_bar + 2;           // [16 warps][4 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bar + MAX_EPI_WARPS * 4);
   float* s_colsum = reinterpret_cast<float*>(tmem_slot + 4);  // [N] when COLSUM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4 * p.groups);  // one arrival per epilogue warp
     }
-    for (int s = 0; s < MAX_EPI_WARPS; ++s) mbar_init(&in_bar[s], 1);
+    for (int s = 0; s < MAX_EPI_WARPS * 4; ++s) mbar_init(&in_bar[s], 1);
     mbar_fence_init();
   }
   if (COLSUM)
@@ -195,12 +195,139 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
     const int e = warp - 2;
     const int grp = e >> 2;                 // 0 .. GROUPS-1
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if constexpr (IN_KIND != 0) {
+      // ---- element-wise input variants: [32 rows x 32 columns] blocks (64B swizzle) computed IN PLACE in a ring of four
+      // 2 KB buffers per warp: the input block arrives by TMA three blocks ahead of its use, the result overwrites it
+      // and leaves with a TMA store; a buffer is refilled once the store issued one block earlier has read it.
+      constexpr int NBUF = 4, BUF_BYTES = 32 * 64;
+      unsigned char* stb = staging + (size_t)e * (2 * WARP_STAGE_BYTES);
+      uint64_t* my_in = &in_bar[e * NBUF];
+      const int n_blocks = (p.block_n + 31) / 32;
+      const int total_blocks = my_tiles * n_blocks;
+      auto block_coords = [&](int b, int& col0, int& row0) {
+        const int tl = b / n_blocks, cb = b - tl * n_blocks;
+        const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+        col0 = (t % p.tiles_n) * p.block_n + cb * 32;
+        row0 = (t / p.tiles_n) * BLOCK_M + q * 32;
+      };
+      auto issue_in = [&](int b, int buf) {
+        int c0, r0;
+        block_coords(b, c0, r0);
+        mbar_expect_tx(&my_in[buf], BUF_BYTES);
+        tma_load_2d(stb + buf * BUF_BYTES, &tmIn, &my_in[buf], c0, r0);
+      };
+      if (lane == 0)
+        for (int k = 0; k < NBUF - 1; ++k)
+          if (grp + k * GROUPS < total_blocks) issue_in(grp + k * GROUPS, k);
+      const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+      int b = grp, i = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+        const int m0 = (t / p.tiles_n) * BLOCK_M, n0 = (t % p.tiles_n) * p.block_n;
+        const uint32_t as = tl & 1u, aph = (tl >> 1) & 1u;
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < p.M;
+        float rs = 1.f;
+        if (SCALE) rs = (g.row_scale && row_ok) ? g.row_scale[m / g.rows_per_group] : 1.f;
+        mbar_wait(&tfull_bar[as], aph);
+        tcgen05_fence_after();
+        const uint32_t trow = tmem_base + as * TMEM_STAGE_COLS + ((uint32_t)(q * 32) << 16);
+        const int b_end = (tl + 1) * n_blocks;
+        for (; b < b_end; b += GROUPS, ++i) {
+          const int cb = b - tl * n_blocks;
+          const int nb0 = n0 + cb * 32;
+          const int ncols = min(32, p.block_n - cb * 32);
+          const int buf = i & (NBUF - 1);
+          unsigned char* st = stb + buf * BUF_BYTES;
+          uint32_t acc[32];
+          tmem_ld32_nowait(trow + cb * 32, acc);
+          mbar_wait(&my_in[buf], (uint32_t)(i >> 2) & 1u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = nb0 + j * 8;
+            const uint32_t soff = (uint32_t)(lane * 64) + ((((uint32_t)j) ^ sw) << 4);
+            float vv[8], u[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) vv[k] = __uint_as_float(acc[j * 8 + k]);
+            if (g.bias && n < p.N) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n) + 1);
+              vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
+              vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
+            }
+            unpack8(*reinterpret_cast<const uint4*>(st + soff), u);
+            if (IN_KIND == 2) {
+              if (ACT == LNX_ACT_GELU) {
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                  const float2 r = __fmul2_rn(make_float2(vv[k], vv[k + 1]), gelu_grad_tanh3_x2(make_float2(u[k], u[k + 1])));
+                  vv[k] = r.x;
+                  vv[k + 1] = r.y;
+                }
+              } else if (ACT == LNX_ACT_RELU) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) vv[k] = u[k] > 0.f ? vv[k] : 0.f;
+              }
+            }
+            if (SCALE) {
+              if (g.col_scale && n < p.N) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(g.col_scale + n));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(g.col_scale + n) + 1);
+                vv[0] *= s0.x * rs; vv[1] *= s0.y * rs; vv[2] *= s0.z * rs; vv[3] *= s0.w * rs;
+                vv[4] *= s1.x * rs; vv[5] *= s1.y * rs; vv[6] *= s1.z * rs; vv[7] *= s1.w * rs;
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) vv[k] *= rs;
+              }
+            }
+            if (IN_KIND == 1) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) vv[k] += u[k];
+            }
+            if (COLSUM && !row_ok) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) vv[k] = 0.f;  // keeps the fused column sums exact at the M edge
+            }
+            *reinterpret_cast<uint4*>(st + soff) = pack8(vv);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (COLSUM) {
+            // column sums of the bf16 values just staged: lane = column, over this warp's 32 rows
+            float cs = 0.f;
+            const uint32_t cj = (uint32_t)(lane >> 3), ce = (uint32_t)(lane & 7) * 2;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const unsigned short w = *reinterpret_cast<const unsigned short*>(st + rr * 64 + ((cj ^ (uint32_t)((rr >> 1) & 3)) << 4) + ce);
+              cs += __uint_as_float((uint32_t)w << 16);
+            }
+            if (lane < ncols && nb0 + lane < p.N) atomicAdd(&s_colsum[nb0 + lane], cs);
+            __syncwarp();
+          }
+          if (lane == 0) {
+            const int row0 = m0 + q * 32;
+            if (row0 < p.M) tma_store_2d(&tmC, st, nb0, row0);
+            tma_store_commit();
+            const int nb = b + (NBUF - 1) * GROUPS;
+            if (nb < total_blocks) {
+              tma_store_wait_read<1>();  // the store issued one block ago has read buffer (i - 1) & 3 = (i + 3) & 3
+              issue_in(nb, (i + NBUF - 1) & (NBUF - 1));
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
+      if (lane == 0) tma_store_wait_all();
+    } else {
     unsigned char* st0 = staging + (size_t)e * p.bufs * WARP_STAGE_BYTES;
     unsigned char* st1 = st0 + WARP_STAGE_BYTES;  // aux output / element-wise input / second C buffer (bufs == 2)
     const bool dbl = !AUX && !IN_KIND && p.bufs == 2;
     uint64_t* my_in = &in_bar[e];
     const int n_blocks = (p.block_n + 63) / 64;
-    const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int total_blocks = my_tiles * n_blocks;
     uint32_t in_cnt = 0, cbuf = 0;
     const int r_sw = lane & 7;
@@ -281,7 +408,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 }
               } else if (ACT == LNX_ACT_GELU) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) vv[i] = gelu_tanh3(vv[i]);
+                for (int i = 0; i < 8; i += 2) {
+                  const float2 r = gelu_tanh3_x2(make_float2(vv[i], vv[i + 1]));
+                  vv[i] = r.x;
+                  vv[i + 1] = r.y;
+                }
               } else if (ACT == LNX_ACT_RELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
@@ -355,6 +486,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
     if (lane == 0) tma_store_wait_all();
+    }  // generic (no element-wise input) path
   }
 
   tcgen05_fence_before();
@@ -375,6 +507,13 @@ bool tmap2d(CUtensorMap* tm, const void* ptr, long long inner, long long outer, 
   const long long strides[1] = {ld};
   const int box[2] = {64, box_outer};
   return make_tmap(tm, ptr, 2, dims, strides, box);
+}
+// [32 rows][32 columns] blocks, 64-byte swizzle (element-wise input variants)
+bool tmap2d_32(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld) {
+  const long long dims[2] = {inner, outer};
+  const long long strides[1] = {ld};
+  const int box[2] = {32, 32};
+  return make_tmap(tm, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int pick_block_n2(int N, bool b_trans) {
@@ -459,7 +598,7 @@ int lnx_gemm_tc2(const GemmArgs& g, float* colsum_out, cudaStream_t st) {
   const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
   const int num_kb = (g.K + BLOCK_K - 1) / BLOCK_K;
   // small K: the epilogue is the whole cost -> 4 groups, double staging; large K: deeper operand ring first
-  auto fixed_bytes = [&](int groups, int bufs) { return 1024 + 4 * groups * bufs * WARP_STAGE_BYTES + 512 + (colsum_out ? g.N * 4 : 0); };
+  auto fixed_bytes = [&](int groups, int bufs) { return 1024 + 4 * groups * bufs * WARP_STAGE_BYTES + 1024 + (colsum_out ? g.N * 4 : 0); };
   const int want = min(4, 2 * num_kb);
   p.groups = num_kb <= 4 ? 4 : 2;
   p.bufs = 2;
@@ -486,11 +625,16 @@ int lnx_gemm_tc2(const GemmArgs& g, float* colsum_out, cudaStream_t st) {
   else ok = tmap2d(&L.tmA, g.A, g.M, g.K, g.lda, 64);
   if (!g.b_trans) ok = ok && tmap2d(&L.tmB, g.B, g.K, g.N, g.ldb, p.block_n);
   else ok = ok && tmap2d(&L.tmB, g.B, g.N, g.K, g.ldb, 64);
-  ok = ok && tmap2d(&L.tmC, g.C, g.N, g.M, g.N, 32);
-  if (g.aux_out) ok = ok && tmap2d(&L.tmAux, g.aux_out, g.N, g.M, g.N, 32);
-  else L.tmAux = L.tmC;
-  if (in_kind) ok = ok && tmap2d(&L.tmIn, in_kind == 1 ? g.residual : g.act_grad_in, g.N, g.M, g.N, 32);
-  else L.tmIn = L.tmC;
+  if (in_kind) {
+    ok = ok && tmap2d_32(&L.tmC, g.C, g.N, g.M, g.N);
+    ok = ok && tmap2d_32(&L.tmIn, in_kind == 1 ? g.residual : g.act_grad_in, g.N, g.M, g.N);
+    L.tmAux = L.tmC;
+  } else {
+    ok = ok && tmap2d(&L.tmC, g.C, g.N, g.M, g.N, 32);
+    if (g.aux_out) ok = ok && tmap2d(&L.tmAux, g.aux_out, g.N, g.M, g.N, 32);
+    else L.tmAux = L.tmC;
+    L.tmIn = L.tmC;
+  }
   if (!ok) return LNX_ERR_UNSUPPORTED;
 
   L.g = g;

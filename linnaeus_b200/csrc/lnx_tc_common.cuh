@@ -157,7 +157,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // bf16 tensor map, 128B swizzle, zero OOB fill. rank 2: [outer][inner]; rank 3: [d2][d1][inner].
 inline bool make_tmap(CUtensorMap* tm, const void* ptr, int rank, const long long* dims, const long long* strides_elems,
-                      const int* box) {
+                      const int* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto enc = get_encode_fn();
   if (!enc) return false;
   cuuint64_t d[3];
@@ -166,7 +166,7 @@ inline bool make_tmap(CUtensorMap* tm, const void* ptr, int rank, const long lon
   for (int i = 0; i < rank; ++i) d[i] = (cuuint64_t)dims[i], b[i] = (cuuint32_t)box[i];
   for (int i = 0; i + 1 < rank; ++i) s[i] = (cuuint64_t)strides_elems[i] * 2;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 

@@ -90,12 +90,21 @@ def rowscale(x2d: torch.Tensor, s: torch.Tensor, rows_per_group: int) -> torch.T
     return out
 
 
-def wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, x_ld: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """dW[N,K] (+)= dy[M,N]^T x[M,K], float32, split over M with atomic accumulation (into ``out`` when given)."""
+def wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, x_ld: int | None = None, out: torch.Tensor | None = None,
+          db_out: torch.Tensor | None = None) -> torch.Tensor:
+    """dW[N,K] (+)= dy[M,N]^T x[M,K] and, when ``db_out`` is given, db[N] += colsum(dy); float32, split over M with
+    atomic accumulation (into ``out`` when given).  bf16 operands run the dedicated tcgen05 kernel (lnx_wgrad: the
+    bias gradient is an extra MMA against a tile of ones); anything else the generic GEMM + a column-sum pass."""
     M, N = dy2d.shape
     K = x2d.shape[1]
     dw = out if out is not None else torch.zeros((N, K), dtype=torch.float32, device=dy2d.device)
+    if (dy2d.dtype == torch.bfloat16 and x2d.dtype == torch.bfloat16 and not FORCE_SIMT and N % 8 == 0 and K % 4 == 0
+            and (x_ld or K) % 8 == 0 and dw.data_ptr() % 16 == 0):
+        call("lnx_wgrad", dy2d.data_ptr(), N, x2d.data_ptr(), x_ld or K, dw.data_ptr(), ptr(db_out), M, N, K, _lib.BF16)
+        return dw
     gemm(dy2d, x2d, N, K, M, a_trans=True, b_trans=True, lda=N, ldb=x_ld or K, out=dw, accumulate=True)
+    if db_out is not None:
+        colsum(dy2d, out=db_out)
     return dw
 
 
@@ -157,20 +166,28 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dpre_w, wc, M, K, N, b_trans=True, ldb=K).view(xshape)
         weight, bias = ctx.params
+        want_db = has_bias and ctx.needs_input_grad[2]
+        sb = _sink(bias) if want_db else None
+        db_buf = None
+        if want_db:
+            db_buf = sb if sb is not None else torch.zeros(N, dtype=torch.float32, device=dpre.device)
+        db_done = False
         if ctx.needs_input_grad[1]:
             sw = _sink(weight)
+            fuse_db = want_db and dpre_w is dpre  # the bias gradient rides on the weight-gradient GEMM
             if sw is not None:
-                wgrad(dpre_w, x2, x_ld=lda, out=sw.view(N, K))
+                wgrad(dpre_w, x2, x_ld=lda, out=sw.view(N, K), db_out=db_buf if fuse_db else None)
                 _grad_done(weight)
             else:
-                dw = wgrad(dpre_w, x2, x_ld=lda)
-        if has_bias and ctx.needs_input_grad[2]:
-            sb = _sink(bias)
+                dw = wgrad(dpre_w, x2, x_ld=lda, db_out=db_buf if fuse_db else None)
+            db_done = fuse_db
+        if want_db:
+            if not db_done:
+                colsum(dpre, out=db_buf)
             if sb is not None:
-                colsum(dpre, out=sb)
                 _grad_done(bias)
             else:
-                db = colsum(dpre)
+                db = db_buf
         return dx, dw, db, None, None, d_res, None, None, None, None
 
 
@@ -226,11 +243,11 @@ class _Mlp2(torch.autograd.Function):
         p_w1, p_b1, p_w2, p_b2, p_cs = ctx.params
         s_w1, s_b1, s_w2, s_b2 = _sink(p_w1), _sink(p_b1), _sink(p_w2), _sink(p_b2)
         db1 = s_b1 if s_b1 is not None else torch.zeros(Hd, dtype=torch.float32, device=dy2.device)
-        dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=act, act_grad_in=pre, colsum_out=db1)  # db1 fused in the epilogue
+        dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=act, act_grad_in=pre)
         d_cs = dw2 = db2 = None
         if col_scale is not None:
-            dw2_raw = wgrad(dy2, h)
-            db2_raw = colsum(dy2)
+            db2_raw = torch.zeros(N, dtype=torch.float32, device=dy2.device)
+            dw2_raw = wgrad(dy2, h, db_out=db2_raw)
             cs = col_scale.detach()
             d_cs = (dw2_raw * w2.detach()).sum(1) + b2.detach() * db2_raw
             if s_w2 is not None:
@@ -244,16 +261,16 @@ class _Mlp2(torch.autograd.Function):
                 _grad_done(p_cs)
                 d_cs = None
         elif s_w2 is not None:
-            wgrad(dy2, h, out=s_w2.view(N, Hd))
-            colsum(dy2, out=s_b2)
+            wgrad(dy2, h, out=s_w2.view(N, Hd), db_out=s_b2)
         else:
-            dw2, db2 = wgrad(dy2, h), colsum(dy2)
+            db2 = torch.zeros(N, dtype=torch.float32, device=dy2.device)
+            dw2 = wgrad(dy2, h, db_out=db2)
         dx = gemm(dpre, w1c, M, K, Hd, b_trans=True, ldb=K).view(xshape) if ctx.needs_input_grad[0] else None
         dw1 = None
         if s_w1 is not None:
-            wgrad(dpre, x2, out=s_w1.view(Hd, K))
+            wgrad(dpre, x2, out=s_w1.view(Hd, K), db_out=db1)  # db1 = colsum(dpre) comes out of the same GEMM
         else:
-            dw1 = wgrad(dpre, x2)
+            dw1 = wgrad(dpre, x2, db_out=db1)
         if s_b1 is not None:
             db1 = None
         for prm, snk in ((p_w1, s_w1), (p_b1, s_b1), (p_w2, s_w2), (p_b2, s_b2)):

@@ -94,3 +94,23 @@ def test_tc_matches_simt_on_same_inputs():
     finally:
         F.FORCE_SIMT = False
     assert rel_err(o1, o2) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 384, 96), (5000, 96, 384), (3000, 768, 192), (2048, 192, 768), (1000, 1536, 384), (777, 1576, 768),
+                                   (256, 768, 768), (130, 64, 48), (64, 8, 4), (9000, 2304, 768)])
+@pytest.mark.parametrize("with_db", [True, False])
+def test_wgrad_kernel(M, N, K, with_db):
+    """lnx_wgrad: dW += dy^T x and db += colsum(dy) (ones-tile MMA), split-K atomics, accumulate semantics."""
+    import linnaeus_b200.functional as F
+
+    dy = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+    ldx = (K + 7) // 8 * 8 + 8  # a column slice of a wider matrix
+    xw = torch.randn(M, ldx, device=DEV).to(torch.bfloat16)
+    x = xw[:, :K]
+    dw = torch.full((N, K), 0.5, device=DEV)
+    db = torch.full((N,), -1.0, device=DEV) if with_db else None
+    F.wgrad(dy, x, x_ld=ldx, out=dw, db_out=db)
+    ref = dy.float().t() @ x.float() + 0.5
+    assert rel_err(dw, ref) < 2e-5
+    if with_db:
+        assert rel_err(db, dy.float().sum(0) - 1.0) < 2e-5

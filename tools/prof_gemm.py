@@ -70,3 +70,24 @@ for (M2, D) in ((B * 200, 384), (B * 53, 768)):
     bench(f"dpre {M2}x{4*D}x{D} act'", lambda: F.gemm(y2, w2_, M2, 4 * D, D, b_trans=True, ldb=4 * D, out=dpre2, act=1, act_grad_in=pre, colsum_out=cs2), 2 * M2 * 4 * D * D)
     bench(f"dx   {M2}x{D}x{4*D}", lambda: F.gemm(dpre2, w1, M2, D, 4 * D, b_trans=True, ldb=D, out=y2), 2 * M2 * 4 * D * D)
     bench(f"dw1  {4*D}x{D}x{M2}", lambda: F.wgrad(dpre2, x), 2 * M2 * 4 * D * D)
+
+# ---- dPre variants at the stage-0 shape (which part of the epilogue costs what)
+bench("dpre gelu' + colsum", lambda: F.gemm(dy, w2, M, N, K, b_trans=True, ldb=N, out=dpre, act=1, act_grad_in=aux, colsum_out=cs), 2 * M * N * K)
+bench("dpre gelu' no colsum", lambda: F.gemm(dy, w2, M, N, K, b_trans=True, ldb=N, out=dpre, act=1, act_grad_in=aux), 2 * M * N * K)
+bench("dpre relu' + colsum", lambda: F.gemm(dy, w2, M, N, K, b_trans=True, ldb=N, out=dpre, act=2, act_grad_in=aux, colsum_out=cs), 2 * M * N * K)
+bench("dpre relu' no colsum", lambda: F.gemm(dy, w2, M, N, K, b_trans=True, ldb=N, out=dpre, act=2, act_grad_in=aux), 2 * M * N * K)
+bench("plain b_trans N=384", lambda: F.gemm(dy, w2, M, N, K, b_trans=True, ldb=N, out=dpre), 2 * M * N * K)
+w2t = w2.t().contiguous()
+bench("plain K-major N=384", lambda: F.gemm(dy, w2t, M, N, K, out=dpre), 2 * M * N * K)
+bench("residual K-major N=384", lambda: F.gemm(dy, w2t, M, N, K, out=dpre, residual=aux), 2 * M * N * K)
+
+# ---- weight-gradient kernels: generic split-K GEMM (v1) vs lnx_wgrad with / without the fused bias gradient
+for (Mr, No, Ki) in ((B * 3136, 384, 96), (B * 3136, 96, 384), (B * 200, 1536, 384), (B * 200, 384, 1536), (B * 53, 3072, 768)):
+    dyw = torch.randn(Mr, No, device=dev).bfloat16()
+    xw = torch.randn(Mr, Ki, device=dev).bfloat16()
+    dww = torch.zeros(No, Ki, device=dev)
+    dbw = torch.zeros(No, device=dev)
+    fl = 2 * Mr * No * Ki
+    bench(f"wgrad v1   {No}x{Ki} K={Mr}", lambda: F.gemm(dyw, xw, No, Ki, Mr, a_trans=True, b_trans=True, lda=No, ldb=Ki, out=dww, accumulate=True), fl)
+    bench(f"lnx_wgrad  {No}x{Ki} K={Mr}", lambda: F.wgrad(dyw, xw, out=dww), fl)
+    bench(f"lnx_wgrad+db {No}x{Ki} K={Mr}", lambda: F.wgrad(dyw, xw, out=dww, db_out=dbw), fl)
