@@ -298,13 +298,19 @@ int lnx_attn_fwd_tc(const void* q, const void* k, const void* v, void* out, floa
 int lnx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, float* dq_f32,
                     void* dk, void* dv, int B, int heads, int N, int hd, cudaStream_t st);
 
+int lnx_attn_fwd_tc2(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd, cudaStream_t st);
+int lnx_attn_bwd_tc2(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, void* dq, void* dk,
+                     void* dv, int B, int heads, int N, int hd, cudaStream_t st);
+
 extern "C" int lnx_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd,
                             int dtype, int force_simt, lnx_stream_t s) {
   LNX_REQUIRE(q && k && v && out && lse, LNX_ERR_NULL);
   LNX_REQUIRE(B > 0 && heads > 0 && N > 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(lnx_aligned16(q) && lnx_aligned16(k) && lnx_aligned16(v) && lnx_aligned16(out), LNX_ERR_ALIGN);
   if (dtype == LNX_BF16 && !force_simt) {
-    const int r = lnx_attn_fwd_tc(q, k, v, out, lse, B, heads, N, hd, (cudaStream_t)s);
+    int r = lnx_attn_fwd_tc2(q, k, v, out, lse, B, heads, N, hd, (cudaStream_t)s);  // persistent, pipelined (N <= 240)
+    if (r != LNX_ERR_UNSUPPORTED) return r;
+    r = lnx_attn_fwd_tc(q, k, v, out, lse, B, heads, N, hd, (cudaStream_t)s);
     if (r != LNX_ERR_UNSUPPORTED) return r;
   }
   return lnx_attn_fwd_simt(q, k, v, out, lse, B, heads, N, hd, dtype, (cudaStream_t)s);
@@ -316,7 +322,10 @@ extern "C" int lnx_attn_bwd(const void* q, const void* k, const void* v, const v
   LNX_REQUIRE(q && k && v && out && dout && lse && dq && dk && dv && delta_ws, LNX_ERR_NULL);
   LNX_REQUIRE(B > 0 && heads > 0 && N > 0, LNX_ERR_SHAPE);
   if (dtype == LNX_BF16 && !force_simt && hd == 64) {
-    // tensor-core path: dQ is accumulated in fp32 (two key tiles per head) in the workspace, then cast
+    // N <= 256: one CTA per (batch, head), dQ accumulated in TMEM and written once as bf16
+    const int r2 = lnx_attn_bwd_tc2(q, k, v, out, dout, lse, dq, dk, dv, B, heads, N, hd, (cudaStream_t)s);
+    if (r2 != LNX_ERR_UNSUPPORTED) return r2;
+    // longer sequences: dQ is accumulated in fp32 (two key tiles per head) in the workspace, then cast
     float* dq32 = delta_ws + (((long long)B * heads * N + 3) / 4) * 4;  // keep the accumulator 16-byte aligned
     const long long n = (long long)B * heads * N * hd;
     cudaError_t e = cudaMemsetAsync(dq32, 0, sizeof(float) * n, (cudaStream_t)s);
