@@ -9,6 +9,9 @@
 // sum of dY -- no epilogue arithmetic, no separate reduction kernel over dY, +16/block_n tensor time.
 //
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM lane quarters).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "lnx_gemm.cuh"
 #include "lnx_tc_common.cuh"
 
@@ -187,27 +190,47 @@ extern "C" int lnx_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx
   if (!lnx_aligned16(dy) || !lnx_aligned16(x) || !lnx_aligned16(dw)) return LNX_ERR_ALIGN;
   cudaStream_t st = (cudaStream_t)s;
 
-  // One accumulator tile per CTA.  Larger per-CTA footprints (mt x nt tiles) would read dY / X exactly once, but the
-  // split-K partials leave through fp32 atomics (measured ~0.4 TB/s under 148-way contention) and that tail grows with
-  // the per-CTA accumulator size, while the re-reads of the smaller operand by neighbouring CTAs hit in L2: measured
-  // on B200, 3 x [128 x 128] per CTA ran the 96 -> 384 shape in 0.22 ms against 0.157 ms for single tiles.
+  // Accumulator tiles per CTA (mt x nt tiles of [128 x block_n], TMEM budget 512 columns) -- measured on B200
+  // (tools/prof_wgrad2.py sweeps, B = 256 shapes):
+  //   K >= 321 (two 192-column tiles, one A tile feeds both)   1 x 2 x 192, one CTA / SM   1536x384: 0.118 -> 0.082 ms
+  //   K  = 192                                                  2 x 1 x 192, one CTA / SM    768x192: 0.118 -> 0.099 ms
+  //   K  =  96 (HBM bound: every byte of dY and X read once)    3 x 1 x 128, one CTA / SM     384x96: 0.190 -> 0.163 ms
+  // Anything else keeps one tile per CTA with two co-resident CTAs per SM.  Bigger footprints lose again: the split-K
+  // partials leave through fp32 atomics and that tail grows with the accumulator size per CTA.
   WgParams p;
   p.M = (int)M; p.N = N; p.K = K; p.has_db = db ? 1 : 0;
   const int tiles_m = (N + BLOCK_M - 1) / BLOCK_M;
   const int kpad = ((K + 63) / 64) * 64;
   p.mt = 1; p.nt = 1;
+  int ctas_per_sm = 2;
   if (kpad <= 192) p.block_n = kpad;
-  else p.block_n = (K % 192 == 0) ? 192 : 128;  // <= 192: the db variant issues N = block_n + 16 <= 256
+  else p.block_n = (kpad % 192 == 0) ? 192 : 128;  // <= 192: the db variant issues N = block_n + 16 <= 256
+  if (kpad >= 2 * p.block_n) {
+    p.nt = 2;
+    ctas_per_sm = 1;
+  } else if (p.block_n == 192 && tiles_m >= 2) {
+    p.mt = 2;
+    ctas_per_sm = 1;
+  } else if (p.block_n == 128 && tiles_m >= 3) {
+    p.mt = 3;
+    ctas_per_sm = 1;
+  }
+  if (const char* e = getenv("LNX_WGRAD_CFG")) {  // experiments: "mt,nt,bn,ctas_per_sm"
+    int a, b2, c, d;
+    if (sscanf(e, "%d,%d,%d,%d", &a, &b2, &c, &d) == 4) {
+      p.mt = a; p.nt = b2; p.block_n = c; ctas_per_sm = d;
+    }
+  }
   const int groups_m = (tiles_m + p.mt - 1) / p.mt;
   p.groups_n = (kpad + p.nt * p.block_n - 1) / (p.nt * p.block_n);
   p.tile_cols = p.block_n + (db ? DB_COLS : 0);
   const int acc = p.mt * p.nt * p.tile_cols;
   p.tmem_cols = acc <= 128 ? 128 : (acc <= 256 ? 256 : 512);
   const int stage = p.mt * 2 * BLK_BYTES + p.nt * (p.block_n / 64) * BLK_BYTES + ONES_BYTES;
-  p.stages = max(2, min(6, (110 * 1024 - 4096) / stage));  // <= 110 KB: two CTAs per SM
+  p.stages = max(2, min(6, ((ctas_per_sm == 2 ? 110 : 220) * 1024 - 4096) / stage));  // <= 110 KB: two CTAs per SM
   const int num_kb = (int)((M + BLOCK_K - 1) / BLOCK_K);
   const int ctas_xy = groups_m * p.groups_n;
-  int splits = max(1, min(num_kb / 8, (2 * kNumSMs + ctas_xy - 1) / ctas_xy));  // two co-resident CTAs per SM
+  int splits = max(1, min(num_kb / 8, ctas_per_sm == 2 ? (2 * kNumSMs + ctas_xy - 1) / ctas_xy : kNumSMs / ctas_xy));
   p.kb_per_split = (num_kb + splits - 1) / splits;
   splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   const size_t smem = (size_t)p.stages * stage + 4096;
