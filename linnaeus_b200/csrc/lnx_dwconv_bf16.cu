@@ -9,9 +9,10 @@
 // warp reads are 7 pixels = 448 bytes apart, i.e. on disjoint shared-memory banks.
 //
 // Work item = one 14x14 output tile of one image x one 32-channel chunk.  CTAs are persistent per channel chunk
-// and double buffered: one thread issues the TMA load (4-D tensor map over [B][H][W][C]; negative / overhanging
-// coordinates are zero filled by the hardware = the conv padding) of the NEXT 20x20 halo tile while all warps
-// compute the current one, so no instruction is spent on staging.  The weight-gradient kernel keeps 49 fp32x2
+// and double buffered: a producer warp issues the TMA loads (4-D tensor map over [B][H][W][C]; negative /
+// overhanging coordinates are zero filled by the hardware = the conv padding) of the NEXT 20x20 halo tile while the
+// seven compute warps work on the current one.  There is no CTA-wide barrier in the steady state: buffers are
+// handed over with full / empty mbarriers, so compute warps drift freely by up to one tile.  The weight-gradient kernel keeps 49 fp32x2
 // partial sums per lane in registers across all tiles the CTA visits.
 #include "lnx_common.cuh"
 #include "lnx_tc_common.cuh"
@@ -23,8 +24,9 @@ namespace {
 
 constexpr int TILE = 14;
 constexpr int HALO = TILE + 6;  // 20
-constexpr int NWARPS = 7;       // warp w -> tile rows 2w, 2w+1
-constexpr int NTHREADS = NWARPS * 32;
+constexpr int NWARPS = 7;       // compute warp w -> tile rows 2w, 2w+1
+constexpr int NCOMPUTE = NWARPS * 32;
+constexpr int NTHREADS = NCOMPUTE + 32;  // + one producer warp (TMA)
 constexpr int PW = 16;          // channel pairs per pixel of a chunk
 constexpr int CC = 2 * PW;      // 32 channels per chunk
 constexpr int HALO_BYTES = HALO * HALO * CC * 2;  // 25600
@@ -63,24 +65,36 @@ __global__ void __launch_bounds__(NTHREADS, 3)
   unsigned char* tiles = smem_raw;                                              // [2][20][20][CC] bf16
   float2* wsm = reinterpret_cast<float2*>(smem_raw + 2 * HALO_BYTES);           // [49][PW]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * HALO_BYTES + 49 * CC * 4);  // [2]
+  uint64_t* empty = full + 2;                                                   // [2]
 
   const int c0 = blockIdx.y * CC;
   const int total = B * tiles_h * tiles_w;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], NWARPS);
+    }
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) reinterpret_cast<float*>(wsm)[i] = w49c[(i / CC) * C + c0 + (i % CC)];
   __syncthreads();
-  if (threadIdx.x == 0 && (int)blockIdx.x < total) {
-    const TileCoord tc = tile_coord(blockIdx.x, tiles_w, tiles_h);
-    mbar_expect_tx(&full[0], HALO_BYTES);
-    tma_load_4d(tiles, &tmX, &full[0], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
-  }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == NWARPS) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait_relaxed(&empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
+        mbar_expect_tx(&full[buf], HALO_BYTES);
+        tma_load_4d(tiles + buf * HALO_BYTES, &tmX, &full[buf], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
+      }
+    }
+    return;
+  }
   const int p = lane & (PW - 1);
   const int col0 = (lane >> 4) * 7;
   const int orow0 = warp * 2;
@@ -90,17 +104,11 @@ __global__ void __launch_bounds__(NTHREADS, 3)
   int it = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
     const int buf = it & 1;
-    const int tn = t + gridDim.x;
-    if (threadIdx.x == 0 && tn < total) {  // buffer buf^1 was released by the barrier that ended the previous iteration
-      const TileCoord tc = tile_coord(tn, tiles_w, tiles_h);
-      mbar_expect_tx(&full[buf ^ 1], HALO_BYTES);
-      tma_load_4d(tiles + (buf ^ 1) * HALO_BYTES, &tmX, &full[buf ^ 1], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
-    }
     const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
-    mbar_wait(&full[buf], (it >> 1) & 1);
+    mbar_wait(&full[buf], ((uint32_t)it >> 1) & 1u);
 
+    float2 acc[2][7];
     if (tc.h0 + orow0 < H) {
-      float2 acc[2][7];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
@@ -125,6 +133,11 @@ __global__ void __launch_bounds__(NTHREADS, 3)
           }
         }
       }
+    }
+    // this warp no longer reads tiles[buf]: hand it back to the producer before the (slow) global stores
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[buf]);
+    if (tc.h0 + orow0 < H) {
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int hh = tc.h0 + orow0 + rr;
@@ -137,7 +150,6 @@ __global__ void __launch_bounds__(NTHREADS, 3)
         }
       }
     }
-    __syncthreads();  // every warp is done with tiles[buf]: it may be refilled by the next iteration's TMA
   }
 }
 
@@ -150,6 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
   unsigned char* stages = smem_raw;                                        // [2]{x halo [20][20][CC], dy [14][14][CC]}
   float* red = reinterpret_cast<float*>(smem_raw + 2 * STAGE);             // [50][CC]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * STAGE + 50 * CC * 4);
+  uint64_t* empty = full + 2;
 
   const int c0 = blockIdx.y * CC;
   const int total = B * tiles_h * tiles_w;
@@ -159,67 +172,76 @@ __global__ void __launch_bounds__(NTHREADS, 2)
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmG);
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], NWARPS);
+    }
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < 50 * CC; i += NTHREADS) red[i] = 0.f;
   __syncthreads();
-  auto issue = [&](int t, int buf) {
-    const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
-    unsigned char* st = stages + buf * STAGE;
-    mbar_expect_tx(&full[buf], HALO_BYTES + CENTER_BYTES);
-    tma_load_4d(st, &tmX, &full[buf], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
-    tma_load_4d(st + HALO_BYTES, &tmG, &full[buf], c0, tc.w0, tc.h0, tc.b);
-  };
-  if (threadIdx.x == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
 
   float2 wacc[49];
   float2 bacc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < 49; ++k) wacc[k] = make_float2(0.f, 0.f);
-
-  int it = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-    const int buf = it & 1;
-    if (threadIdx.x == 0 && t + (int)gridDim.x < total) issue(t + gridDim.x, buf ^ 1);
-    mbar_wait(&full[buf], (it >> 1) & 1);
-    const unsigned char* st = stages + buf * STAGE;
-#pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {  // strips of 7 outputs: 13 tile loads feed 49 FFMA2 per filter row
-      const int orow = warp * 2 + rr;
-      float2 g[7];
-      const uint32_t* gp = reinterpret_cast<const uint32_t*>(st + HALO_BYTES) + ((orow * TILE + col0) * PW + p);
-#pragma unroll
-      for (int o = 0; o < 7; ++o) {
-        g[o] = unpack_bf16x2(gp[o * PW]);  // rows / columns beyond the image were zero filled
-        bacc.x += g[o].x;
-        bacc.y += g[o].y;
+  if (warp == NWARPS) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait_relaxed(&empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
+        unsigned char* st = stages + buf * STAGE;
+        mbar_expect_tx(&full[buf], HALO_BYTES + CENTER_BYTES);
+        tma_load_4d(st, &tmX, &full[buf], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
+        tma_load_4d(st + HALO_BYTES, &tmG, &full[buf], c0, tc.w0, tc.h0, tc.b);
       }
-      const uint32_t* tp = reinterpret_cast<const uint32_t*>(st) + ((orow * HALO + col0) * PW + p);
+    }
+  } else {
 #pragma unroll
-      for (int kh = 0; kh < 7; ++kh) {
-        const uint32_t* rowp = tp + kh * HALO * PW;
+    for (int k = 0; k < 49; ++k) wacc[k] = make_float2(0.f, 0.f);
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&full[buf], ((uint32_t)it >> 1) & 1u);
+      const unsigned char* st = stages + buf * STAGE;
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {  // strips of 7 outputs: 13 tile loads feed 49 FFMA2 per filter row
+        const int orow = warp * 2 + rr;
+        float2 g[7];
+        const uint32_t* gp = reinterpret_cast<const uint32_t*>(st + HALO_BYTES) + ((orow * TILE + col0) * PW + p);
 #pragma unroll
-        for (int ix = 0; ix < 13; ++ix) {
-          const float2 v = unpack_bf16x2(rowp[ix * PW]);
+        for (int o = 0; o < 7; ++o) {
+          g[o] = unpack_bf16x2(gp[o * PW]);  // rows / columns beyond the image were zero filled
+          bacc.x += g[o].x;
+          bacc.y += g[o].y;
+        }
+        const uint32_t* tp = reinterpret_cast<const uint32_t*>(st) + ((orow * HALO + col0) * PW + p);
 #pragma unroll
-          for (int kw = 0; kw < 7; ++kw) {
-            const int o = ix - kw;
-            if (o >= 0 && o < 7) wacc[kh * 7 + kw] = ffma2(v, g[o], wacc[kh * 7 + kw]);
+        for (int kh = 0; kh < 7; ++kh) {
+          const uint32_t* rowp = tp + kh * HALO * PW;
+#pragma unroll
+          for (int ix = 0; ix < 13; ++ix) {
+            const float2 v = unpack_bf16x2(rowp[ix * PW]);
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+              const int o = ix - kw;
+              if (o >= 0 && o < 7) wacc[kh * 7 + kw] = ffma2(v, g[o], wacc[kh * 7 + kw]);
+            }
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[buf]);
     }
-    __syncthreads();
-  }
 #pragma unroll
-  for (int k = 0; k < 49; ++k) {
-    atomicAdd(&red[k * CC + 2 * p], wacc[k].x);
-    atomicAdd(&red[k * CC + 2 * p + 1], wacc[k].y);
+    for (int k = 0; k < 49; ++k) {
+      atomicAdd(&red[k * CC + 2 * p], wacc[k].x);
+      atomicAdd(&red[k * CC + 2 * p + 1], wacc[k].y);
+    }
+    atomicAdd(&red[49 * CC + 2 * p], bacc.x);
+    atomicAdd(&red[49 * CC + 2 * p + 1], bacc.y);
   }
-  atomicAdd(&red[49 * CC + 2 * p], bacc.x);
-  atomicAdd(&red[49 * CC + 2 * p + 1], bacc.y);
   __syncthreads();
   for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) atomicAdd(dw49c + (i / CC) * C + c0 + (i % CC), red[i]);
   if (dbias)
