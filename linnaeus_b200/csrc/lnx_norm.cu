@@ -288,7 +288,7 @@ struct RawVec<4> {
 // VEC = bf16 elements per thread slot (8 or 4): 4 halves the 2 * NV * VEC per-thread gamma / beta accumulators so
 // that three CTAs stay resident at C = 96 / 192 / 384.
 template <int NV, int LANES, int VEC>
-__global__ void __launch_bounds__(256, (VEC == 4 ? 3 : 1))
+__global__ void __launch_bounds__(256, (VEC == 4 ? 2 : 1))
     ln_bwd_bf16_kernel(const void* __restrict__ dy_, const void* __restrict__ x_, const float* __restrict__ w, const float* __restrict__ mean,
                        const float* __restrict__ rstd, void* __restrict__ dx_, float* __restrict__ dw, float* __restrict__ db, long long rows) {
   typedef typename RawVec<VEC>::type RV;
@@ -314,36 +314,45 @@ __global__ void __launch_bounds__(256, (VEC == 4 ? 3 : 1))
   for (int j = 0; j < NV; ++j)
 #pragma unroll
     for (int i = 0; i < VEC; ++i) dw_acc[j][i] = 0.f, db_acc[j][i] = 0.f;
-  RV xc[NV], gc[NV], xn[NV], gn[NV];
-  float mu = 0.f, rs = 0.f, mun = 0.f, rsn = 0.f;
+  // two rows of lookahead: the loads of rows r + stride and r + 2 stride are in flight while row r is reduced
+  RV xc[NV], gc[NV], xn[NV], gn[NV], xm[NV], gm[NV];
+  float mu = 0.f, rs = 0.f, mun = 0.f, rsn = 0.f, mum = 0.f, rsm = 0.f;
   {
     const long long row = (long long)blockIdx.x * GPB + gid;
     const bool ok = row < rows;
+    const long long row1 = row + stride;
+    const bool ok1 = row1 < rows;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {  // rows past the end read row 0 and get rstd = 0: every contribution vanishes
       xc[j] = __ldg(x + (ok ? row : 0) * CV + lane + j * LANES);
       gc[j] = __ldg(dy + (ok ? row : 0) * CV + lane + j * LANES);
+      xn[j] = __ldg(x + (ok1 ? row1 : 0) * CV + lane + j * LANES);
+      gn[j] = __ldg(dy + (ok1 ? row1 : 0) * CV + lane + j * LANES);
     }
     if (ok) {
       mu = mean[row];
       rs = rstd[row];
+    }
+    if (ok1) {
+      mun = mean[row1];
+      rsn = rstd[row1];
     }
   }
   // the loop bound is CTA-uniform (the shuffles below are full-warp)
   for (long long base = (long long)blockIdx.x * GPB; base < rows; base += stride) {
     const long long row = base + gid;
     const bool valid = row < rows;
-    const long long nrow = row + stride;
-    mun = 0.f;
-    rsn = 0.f;
-    if (nrow < rows) {
+    const long long mrow = row + 2 * stride;
+    mum = 0.f;
+    rsm = 0.f;
+    if (mrow < rows) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        xn[j] = __ldg(x + nrow * CV + lane + j * LANES);
-        gn[j] = __ldg(dy + nrow * CV + lane + j * LANES);
+        xm[j] = __ldg(x + mrow * CV + lane + j * LANES);
+        gm[j] = __ldg(dy + mrow * CV + lane + j * LANES);
       }
-      mun = mean[nrow];
-      rsn = rstd[nrow];
+      mum = mean[mrow];
+      rsm = rstd[mrow];
     }
     // pass 1: row statistics and the per-column gamma / beta partial sums (nothing kept but the raw vectors)
     float s1 = 0.f, s2 = 0.f;
@@ -387,9 +396,13 @@ __global__ void __launch_bounds__(256, (VEC == 4 ? 3 : 1))
     for (int j = 0; j < NV; ++j) {
       xc[j] = xn[j];
       gc[j] = gn[j];
+      xn[j] = xm[j];
+      gn[j] = gm[j];
     }
     mu = mun;
     rs = rsn;
+    mun = mum;
+    rsn = rsm;
   }
   // lanes of different groups hold partial sums of the same columns: fold through shared memory, then one global
   // atomic per column per CTA
@@ -452,7 +465,7 @@ int ln_bwd_fast(const void* dy, const void* x, const float* w, const float* mean
 #define LNX_B(NVV, LL, VV)                                                                                                   \
   {                                                                                                                          \
     const int gpb = 256 / LL;                                                                                                \
-    const int blocks = (int)max(1LL, min((long long)kNumSMs * (VV == 4 ? 3 : 2), (rows + gpb - 1) / gpb));                    \
+    const int blocks = (int)max(1LL, min((long long)kNumSMs * 2, (rows + gpb - 1) / gpb));                    \
     ln_bwd_bf16_kernel<NVV, LL, VV><<<blocks, 256, 0, st>>>(dy, x, w, mean, rstd, dx, dw, db, rows);                          \
   }
   if (C % 12 == 0 && (C / 12 == 8 || C / 12 == 16 || C / 12 == 32)) {  // 4-element slots, 3 per thread: C = 96 / 192 / 384

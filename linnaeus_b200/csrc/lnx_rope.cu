@@ -8,6 +8,37 @@ using namespace lnx;
 
 namespace {
 
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float* x);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float* x) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<bf16>(const bf16* p, float* x) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  x[0] = __uint_as_float(r.x << 16); x[1] = __uint_as_float(r.x & 0xffff0000u);
+  x[2] = __uint_as_float(r.y << 16); x[3] = __uint_as_float(r.y & 0xffff0000u);
+  x[4] = __uint_as_float(r.z << 16); x[5] = __uint_as_float(r.z & 0xffff0000u);
+  x[6] = __uint_as_float(r.w << 16); x[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float* x);
+template <>
+__device__ __forceinline__ void st8<float>(float* p, const float* x) {
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(x[4], x[5], x[6], x[7]);
+}
+template <>
+__device__ __forceinline__ void st8<bf16>(bf16* p, const float* x) {
+  uint4 raw;
+  __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
 __global__ void rope_table_kernel(const float* __restrict__ freqs, float* __restrict__ cos_out, float* __restrict__ sin_out, int H,
                                   int W, int heads, int half) {
   const int total = H * W * heads * half;
@@ -99,16 +130,17 @@ __global__ void rope_qk_bwd_kernel(const T* __restrict__ dq, const T* __restrict
       const T* gp = gsrc + ((((long long)b * heads + h) * N + n) * hd) + ch * 8;
       const long long o = ((((long long)b * N + n) * 3 + which) * heads + h) * hd + ch * 8;
       float g[8], x[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) g[e] = to_f32(gp[e]);
+      ld8<T>(gp, g);
       if (which < 2 && img) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = to_f32(qkv[o + e]);
+        ld8<T>(qkv + o, x);
 #pragma unroll
         for (int e = 0; e < 8; ++e) dth[e >> 1] += g[e] * x[e] * sc * (-sn[e >> 1]);
       }
+      if (which < 2) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dqkv[o + e] = from_f32<T>(which < 2 ? g[e] * c[e >> 1] * sc : g[e]);
+        for (int e = 0; e < 8; ++e) g[e] *= c[e >> 1] * sc;
+      }
+      st8<T>(dqkv + o, g);
     }
     if (which < 2 && img) {
       float* dst = dtheta + ((long long)(n - n_extra) * heads + h) * (hd / 2) + ch * 4;
@@ -119,17 +151,22 @@ __global__ void rope_qk_bwd_kernel(const T* __restrict__ dq, const T* __restrict
 }
 
 __global__ void rope_freq_grad_kernel(const float* __restrict__ dtheta, float* __restrict__ dfreqs, int H, int W, int heads, int half) {
-  // one thread per (h, j); loops over the grid positions
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per (h, j): lanes stride over the grid positions, shuffle reduction
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= heads * half) return;
   float gx = 0.f, gy = 0.f;
-  for (int n = 0; n < H * W; ++n) {
+  for (int n = lane; n < H * W; n += 32) {
     const float d = dtheta[(long long)n * heads * half + i];
     gx += (float)(n % W) * d;
     gy += (float)(n / W) * d;
   }
-  atomicAdd(dfreqs + i, gx);
-  atomicAdd(dfreqs + heads * half + i, gy);
+  gx = warp_sum(gx);
+  gy = warp_sum(gy);
+  if (lane == 0) {
+    atomicAdd(dfreqs + i, gx);
+    atomicAdd(dfreqs + heads * half + i, gy);
+  }
 }
 
 }  // namespace
@@ -166,6 +203,7 @@ extern "C" int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, c
                                lnx_stream_t s) {
   LNX_REQUIRE(dq && dk && dv && qkv && cos_tab && sin_tab && dqkv && dtheta, LNX_ERR_NULL);
   LNX_REQUIRE(B > 0 && N > n_extra && heads > 0 && hd % 8 == 0, LNX_ERR_SHAPE);
+  LNX_REQUIRE(lnx_aligned16(dq) && lnx_aligned16(dk) && lnx_aligned16(dv) && lnx_aligned16(qkv) && lnx_aligned16(dqkv), LNX_ERR_ALIGN);
   const int work = 3 * heads * (hd / 8);
   const int threads = min(256, ((work + 31) / 32) * 32);
   int by = max(1, min(B, (kNumSMs * 8 + N - 1) / N));
@@ -186,7 +224,7 @@ extern "C" int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, c
 extern "C" int lnx_rope_freq_grad(const float* dtheta, float* dfreqs, int H, int W, int heads, int half, lnx_stream_t s) {
   LNX_REQUIRE(dtheta && dfreqs, LNX_ERR_NULL);
   const int n = heads * half;
-  rope_freq_grad_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)s>>>(dtheta, dfreqs, H, W, heads, half);
+  rope_freq_grad_kernel<<<(n * 32 + 127) / 128, 128, 0, (cudaStream_t)s>>>(dtheta, dfreqs, H, W, heads, half);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
