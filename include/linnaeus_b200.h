@@ -81,14 +81,15 @@ int lnx_act_bwd(const void* dy, const void* pre, void* out, int64_t n, int act, 
 int lnx_layernorm_fwd(const void* x, const float* w, const float* b, const void* residual, void* y, float* mean, float* rstd,
                       int64_t rows, int C, float eps, int dtype, lnx_stream_t s);
 /* dx = LN backward; dw[C] += , db[C] += */
-int lnx_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, void* dx,
+int lnx_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, const void* dres, void* dx,
                       float* dw, float* db, int64_t rows, int C, int dtype, lnx_stream_t s);
 
 /* ---- depthwise 7x7 (pad 3) on NHWC ------------------------------------- */
 /* w49c is the Conv2d weight [C,1,7,7] transposed to [49,C]; bias may be NULL.
  * The data gradient is the same call with the taps reversed and bias = NULL.
  * R/models/blocks/convnext.py:56-58,76. */
-int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, int dtype, lnx_stream_t s);
+int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, const void* residual, void* y, int B, int H, int W, int C, int dtype,
+                    lnx_stream_t s);
 /* dw49c[49,C] += , dbias[C] += */
 int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, int dtype, lnx_stream_t s);
 

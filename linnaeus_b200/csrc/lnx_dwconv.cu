@@ -67,8 +67,9 @@ __device__ __forceinline__ void load_tile(T* tile, const T* __restrict__ src, in
 // ------------------------------------------------------------------ forward
 template <typename T, int CPL>
 __global__ void __launch_bounds__(NWARPS * 32) dwconv7_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w49c,
-                                                                   const float* __restrict__ bias, T* __restrict__ y, int B, int H,
-                                                                   int W, int C, int tiles_w, int tiles_h) {
+                                                                   const float* __restrict__ bias, const T* __restrict__ res,
+                                                                   T* __restrict__ y, int B, int H, int W, int C, int tiles_w,
+                                                                   int tiles_h) {
   constexpr int CC = 32 * CPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);                                     // [20][20][CC]
@@ -135,7 +136,12 @@ __global__ void __launch_bounds__(NWARPS * 32) dwconv7_fwd_kernel(const T* __res
       for (int o = 0; o < TILE; ++o) {
         const int ww = w0 + o;
         if (ww < W) {
-          T* dst = y + (((long long)b * H + hh) * W + ww) * C + c0 + cl;
+          const long long off = (((long long)b * H + hh) * W + ww) * C + c0 + cl;
+          T* dst = y + off;
+          if (res) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) acc[rr][o][q] += to_f32(res[off + q]);
+          }
           if constexpr (CPL == 2) {
             if constexpr (sizeof(T) == 2) {
               *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(acc[rr][o][0], acc[rr][o][1]);
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(NWARPS * 32) dwconv7_wgrad_kernel(const T* __r
 }
 
 template <typename T, int CPL>
-int fwd_launch(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, cudaStream_t st) {
+int fwd_launch(const void* x, const float* w49c, const float* bias, const void* res, void* y, int B, int H, int W, int C, cudaStream_t st) {
   constexpr int CC = 32 * CPL;
   const int tiles_w = (W + TILE - 1) / TILE, tiles_h = (H + TILE - 1) / TILE;
   const size_t smem = sizeof(T) * HALO * HALO * CC + sizeof(float) * 49 * CC;
@@ -239,7 +245,7 @@ int fwd_launch(const void* x, const float* w49c, const float* bias, void* y, int
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return lnx_set_cuda_error(e);
   dim3 grid(B * tiles_h * tiles_w, C / CC);
-  kern<<<grid, NWARPS * 32, smem, st>>>((const T*)x, w49c, bias, (T*)y, B, H, W, C, tiles_w, tiles_h);
+  kern<<<grid, NWARPS * 32, smem, st>>>((const T*)x, w49c, bias, (const T*)res, (T*)y, B, H, W, C, tiles_w, tiles_h);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
@@ -264,17 +270,20 @@ int wgrad_launch(const void* x, const void* dy, float* dw, float* db, int B, int
 }  // namespace
 
 // bf16: packed-fp32x2 (FFMA2) kernels of lnx_dwconv_bf16.cu
-int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, cudaStream_t st);
+int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, const void* res, void* y, int B, int H, int W, int C,
+                         cudaStream_t st);
 int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, cudaStream_t st);
 
-extern "C" int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, int dtype, lnx_stream_t s) {
+extern "C" int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, const void* residual, void* y, int B, int H, int W, int C,
+                               int dtype, lnx_stream_t s) {
   LNX_REQUIRE(x && w49c && y, LNX_ERR_NULL);
   LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(y), LNX_ERR_ALIGN);
   cudaStream_t st = (cudaStream_t)s;
   const bool pair = (C % 64 == 0);
-  if (dtype == LNX_F32) return pair ? fwd_launch<float, 2>(x, w49c, bias, y, B, H, W, C, st) : fwd_launch<float, 1>(x, w49c, bias, y, B, H, W, C, st);
-  if (dtype == LNX_BF16) return lnx_dwconv7_fwd_bf16(x, w49c, bias, y, B, H, W, C, st);
+  if (dtype == LNX_F32)
+    return pair ? fwd_launch<float, 2>(x, w49c, bias, residual, y, B, H, W, C, st) : fwd_launch<float, 1>(x, w49c, bias, residual, y, B, H, W, C, st);
+  if (dtype == LNX_BF16) return lnx_dwconv7_fwd_bf16(x, w49c, bias, residual, y, B, H, W, C, st);
   return LNX_ERR_DTYPE;
 }
 

@@ -60,7 +60,7 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_w, int tiles_h)
 // ------------------------------------------------------------------ forward (and data gradient with flipped taps)
 __global__ void __launch_bounds__(NTHREADS, 3)
     dwconv7_fwd_x2_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w49c, const float* __restrict__ bias,
-                          bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h) {
+                          const bf16* __restrict__ res, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* tiles = smem_raw;                                              // [2][20][20][CC] bf16
   float2* wsm = reinterpret_cast<float2*>(smem_raw + 2 * HALO_BYTES);           // [49][PW]
@@ -142,7 +142,17 @@ __global__ void __launch_bounds__(NTHREADS, 3)
       for (int rr = 0; rr < 2; ++rr) {
         const int hh = tc.h0 + orow0 + rr;
         if (hh < H) {
-          bf16* yrow = y + (((long long)tc.b * H + hh) * W + tc.w0 + col0) * C + c0 + 2 * p;
+          const long long off = (((long long)tc.b * H + hh) * W + tc.w0 + col0) * C + c0 + 2 * p;
+          bf16* yrow = y + off;
+          if (res) {  // fused "+ residual" (the skip-connection gradient when this kernel runs as the data gradient)
+#pragma unroll
+            for (int o = 0; o < 7; ++o)
+              if (tc.w0 + col0 + o < W) {
+                const float2 rv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(res + off + (long long)o * C)));
+                acc[rr][o].x += rv.x;
+                acc[rr][o].y += rv.y;
+              }
+          }
 #pragma unroll
           for (int o = 0; o < 7; ++o)
             if (tc.w0 + col0 + o < W)
@@ -262,7 +272,8 @@ bool make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C
 
 }  // namespace
 
-int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, void* y, int B, int H, int W, int C, cudaStream_t st) {
+int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, const void* res, void* y, int B, int H, int W, int C,
+                         cudaStream_t st) {
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 7u)) return LNX_ERR_ALIGN;
   if (C % CC != 0) return LNX_ERR_SHAPE;
   CUtensorMap tmX;
@@ -278,7 +289,7 @@ int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, vo
   const int chunks = C / CC;
   const int total = B * tiles_h * tiles_w;
   const int gx = max(1, min(total, (kNumSMs * 3 + chunks - 1) / chunks));
-  dwconv7_fwd_x2_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
+  dwconv7_fwd_x2_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }

@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
 
 template <typename T, int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w,
-                                                     const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-                                                     float* __restrict__ dw, float* __restrict__ db, long long rows, int C, int lanes) {
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const T* __restrict__ dres, T* __restrict__ dx, float* __restrict__ dw,
+                                                     float* __restrict__ db, long long rows, int C, int lanes) {
   constexpr int V = Vec16<T>::N;
   extern __shared__ float sred[];  // [2][C]
   const int Cv = C / V;
@@ -122,12 +123,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     for (int j = 0; j < NV; ++j) {
       const int cv = lane + j * lanes;
       if (valid && cv < Cv) {
-        Vec16<T> o;
+        Vec16<T> o, rv;
+        if (dres) rv = ld16(dres + row * C + (long long)cv * V);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           const float xh = (xv[j].get(i) - mu) * rs;
           const float gw = gv[j].get(i) * w[cv * V + i];
-          o.set(i, rs * (gw - c1 - xh * c2));
+          float r = rs * (gw - c1 - xh * c2);
+          if (dres) r += rv.get(i);
+          o.set(i, r);
         }
         st16(dx + row * C + (long long)cv * V, o);
       }
@@ -290,8 +294,10 @@ struct RawVec<4> {
 template <int NV, int LANES, int VEC>
 __global__ void __launch_bounds__(256, (VEC == 4 ? 2 : 1))
     ln_bwd_bf16_kernel(const void* __restrict__ dy_, const void* __restrict__ x_, const float* __restrict__ w, const float* __restrict__ mean,
-                       const float* __restrict__ rstd, void* __restrict__ dx_, float* __restrict__ dw, float* __restrict__ db, long long rows) {
+                       const float* __restrict__ rstd, const void* __restrict__ dres_, void* __restrict__ dx_, float* __restrict__ dw,
+                       float* __restrict__ db, long long rows) {
   typedef typename RawVec<VEC>::type RV;
+  const RV* __restrict__ dres = reinterpret_cast<const RV*>(dres_);  // optional: skip-connection gradient added to dx
   const RV* __restrict__ dy = reinterpret_cast<const RV*>(dy_);
   const RV* __restrict__ x = reinterpret_cast<const RV*>(x_);
   RV* __restrict__ dx = reinterpret_cast<RV*>(dx_);
@@ -390,6 +396,12 @@ __global__ void __launch_bounds__(256, (VEC == 4 ? 2 : 1))
         const float xhat = (xh[i] - mu) * rs;
         o[i] = rs * (fmaf(g[i], wv[i], -c1) - xhat * c2);
       }
+      if (dres && valid) {
+        float rv[VEC];
+        RawVec<VEC>::unpack(__ldg(dres + row * CV + cv), rv);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] += rv[i];
+      }
       if (valid) dx[row * CV + cv] = RawVec<VEC>::pack(o);
     }
 #pragma unroll
@@ -459,14 +471,14 @@ int ln_fwd_fast(const void* x, const float* w, const float* b, const void* res, 
   return LNX_OK;
 }
 
-int ln_bwd_fast(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, void* dx, float* dw, float* db,
-                long long rows, int C, cudaStream_t st) {
+int ln_bwd_fast(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, const void* dres, void* dx, float* dw,
+                float* db, long long rows, int C, cudaStream_t st) {
   int nv, lanes;
 #define LNX_B(NVV, LL, VV)                                                                                                   \
   {                                                                                                                          \
     const int gpb = 256 / LL;                                                                                                \
     const int blocks = (int)max(1LL, min((long long)kNumSMs * 2, (rows + gpb - 1) / gpb));                    \
-    ln_bwd_bf16_kernel<NVV, LL, VV><<<blocks, 256, 0, st>>>(dy, x, w, mean, rstd, dx, dw, db, rows);                          \
+    ln_bwd_bf16_kernel<NVV, LL, VV><<<blocks, 256, 0, st>>>(dy, x, w, mean, rstd, dres, dx, dw, db, rows);                          \
   }
   if (C % 12 == 0 && (C / 12 == 8 || C / 12 == 16 || C / 12 == 32)) {  // 4-element slots, 3 per thread: C = 96 / 192 / 384
     if (C == 96) LNX_B(3, 8, 4) else if (C == 192) LNX_B(3, 16, 4) else LNX_B(3, 32, 4)
@@ -525,8 +537,8 @@ int ln_fwd_launch(const void* x, const float* w, const float* b, const void* res
 }
 
 template <typename T>
-int ln_bwd_launch(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, void* dx, float* dw,
-                  float* db, long long rows, int C, cudaStream_t st) {
+int ln_bwd_launch(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, const void* dres, void* dx,
+                  float* dw, float* db, long long rows, int C, cudaStream_t st) {
   constexpr int V = Vec16<T>::N;
   LnPlan p;
   if (C % V != 0 || !ln_plan(C / V, &p)) return LNX_ERR_SHAPE;
@@ -535,7 +547,7 @@ int ln_bwd_launch(const void* dy, const void* x, const float* w, const float* me
   const size_t smem = 2 * (size_t)C * sizeof(float);
 #define LNX_LN_B(NVV)                                                                                                         \
   case NVV:                                                                                                                   \
-    ln_bwd_kernel<T, NVV><<<blocks, 256, smem, st>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, dw, db, rows, C, p.lanes); \
+    ln_bwd_kernel<T, NVV><<<blocks, 256, smem, st>>>((const T*)dy, (const T*)x, w, mean, rstd, (const T*)dres, (T*)dx, dw, db, rows, C, p.lanes); \
     break;
   switch (p.nv) {
     LNX_LN_B(1) LNX_LN_B(2) LNX_LN_B(3) LNX_LN_B(4) LNX_LN_B(8) LNX_LN_B(16)
@@ -562,16 +574,16 @@ extern "C" int lnx_layernorm_fwd(const void* x, const float* w, const float* b, 
   return LNX_ERR_DTYPE;
 }
 
-extern "C" int lnx_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, void* dx,
-                                 float* dw, float* db, int64_t rows, int C, int dtype, lnx_stream_t s) {
+extern "C" int lnx_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, const void* dres,
+                                 void* dx, float* dw, float* db, int64_t rows, int C, int dtype, lnx_stream_t s) {
   LNX_REQUIRE(dy && x && w && mean && rstd && dx && dw && db, LNX_ERR_NULL);
   LNX_REQUIRE(rows > 0 && C > 0, LNX_ERR_SHAPE);
-  LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(dy) && lnx_aligned16(dx), LNX_ERR_ALIGN);
-  if (dtype == LNX_F32) return ln_bwd_launch<float>(dy, x, w, mean, rstd, dx, dw, db, rows, C, (cudaStream_t)s);
+  LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(dy) && lnx_aligned16(dx) && lnx_aligned16(dres), LNX_ERR_ALIGN);
+  if (dtype == LNX_F32) return ln_bwd_launch<float>(dy, x, w, mean, rstd, dres, dx, dw, db, rows, C, (cudaStream_t)s);
   if (dtype == LNX_BF16) {
-    const int r = ln_bwd_fast(dy, x, w, mean, rstd, dx, dw, db, rows, C, (cudaStream_t)s);
+    const int r = ln_bwd_fast(dy, x, w, mean, rstd, dres, dx, dw, db, rows, C, (cudaStream_t)s);
     if (r != LNX_ERR_UNSUPPORTED) return r;
-    return ln_bwd_launch<bf16>(dy, x, w, mean, rstd, dx, dw, db, rows, C, (cudaStream_t)s);
+    return ln_bwd_launch<bf16>(dy, x, w, mean, rstd, dres, dx, dw, db, rows, C, (cudaStream_t)s);
   }
   return LNX_ERR_DTYPE;
 }

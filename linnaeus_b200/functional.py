@@ -286,7 +286,7 @@ def mlp2(x, w1, b1, w2, b2, w1c=None, w2c=None, act="gelu", residual=None, col_s
 # --------------------------------------------------------------------------- LayerNorm
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, eps, residual):
+    def forward(ctx, x, w, b, eps, residual, fork):
         C = x.shape[-1]
         x2 = _c(x).view(-1, C)
         rows = x2.shape[0]
@@ -300,47 +300,62 @@ class _LayerNorm(torch.autograd.Function):
         ctx.params = (w, b)
         ctx.has_res = residual is not None
         ctx.xshape = x.shape
+        if fork:  # second output = the input itself (skip connection): its gradient is added inside the backward kernel
+            return y.view(x.shape), x.view_as(x)
         return y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x2, w, mean, rstd = ctx.saved_tensors
         rows, C = x2.shape
         dy2 = _c(dy).view(rows, C)
+        dres = _c(dskip).view(rows, C) if dskip is not None else None
         dx = torch.empty_like(x2)
         p_w, p_b = ctx.params
         s_w, s_b = _sink(p_w), _sink(p_b)
         direct = s_w is not None and s_b is not None
         dw = s_w if direct else torch.zeros(C, dtype=torch.float32, device=x2.device)
         db = s_b if direct else torch.zeros(C, dtype=torch.float32, device=x2.device)
-        call("lnx_layernorm_bwd", dy2.data_ptr(), x2.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+        call("lnx_layernorm_bwd", dy2.data_ptr(), x2.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(dres), dx.data_ptr(),
              dw.data_ptr(), db.data_ptr(), rows, C, dt(x2))
         if direct:
             _grad_done(p_w)
             _grad_done(p_b)
             dw = db = None
-        return dx.view(ctx.xshape), dw, db, None, (dy if ctx.has_res else None)
+        return dx.view(ctx.xshape), dw, db, None, (dy if ctx.has_res else None), None
 
 
 def layernorm(x, w, b, eps=1e-5, residual=None):
-    return _LayerNorm.apply(x, w, b, eps, residual)
+    return _LayerNorm.apply(x, w, b, eps, residual, False)
+
+
+def layernorm_fork(x, w, b, eps=1e-5):
+    """-> (LN(x), x): use the second output as the skip connection of a pre-norm block (see _LayerNorm.forward)."""
+    return _LayerNorm.apply(x, w, b, eps, None, True)
 
 
 # --------------------------------------------------------------------------- depthwise 7x7
 class _DwConv7(torch.autograd.Function):
+    """Depthwise 7x7.  With ``fork`` the input is also returned as a second output (the skip connection of the
+    ConvNeXt block): its gradient is then added inside the data-gradient kernel instead of by a separate
+    autograd add over the whole activation."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, fork):
         B, H, W, C = x.shape
         x = _c(x)
         w49c = weight.detach().reshape(C, 49).t().contiguous()
         y = torch.empty_like(x)
-        call("lnx_dwconv7_fwd", x.data_ptr(), w49c.data_ptr(), ptr(bias), y.data_ptr(), B, H, W, C, dt(x))
+        call("lnx_dwconv7_fwd", x.data_ptr(), w49c.data_ptr(), ptr(bias), None, y.data_ptr(), B, H, W, C, dt(x))
         ctx.save_for_backward(x, w49c)
         ctx.has_bias = bias is not None
+        ctx.params = (weight, bias)
+        if fork:
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x, w49c = ctx.saved_tensors
         B, H, W, C = x.shape
         dy = _c(dy)
@@ -348,15 +363,21 @@ class _DwConv7(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             wflip = w49c.flip(0).contiguous()
-            call("lnx_dwconv7_fwd", dy.data_ptr(), wflip.data_ptr(), None, dx.data_ptr(), B, H, W, C, dt(x))
+            res = _c(dskip) if dskip is not None else None
+            call("lnx_dwconv7_fwd", dy.data_ptr(), wflip.data_ptr(), None, ptr(res), dx.data_ptr(), B, H, W, C, dt(x))
         dw49c = torch.zeros_like(w49c)
         db = torch.zeros(C, dtype=torch.float32, device=x.device)
         call("lnx_dwconv7_wgrad", x.data_ptr(), dy.data_ptr(), dw49c.data_ptr(), db.data_ptr(), B, H, W, C, dt(x))
-        return dx, dw49c.t().reshape(C, 1, 7, 7), (db if ctx.has_bias else None)
+        return dx, dw49c.t().reshape(C, 1, 7, 7), (db if ctx.has_bias else None), None
 
 
 def dwconv7(x_nhwc, weight, bias):
-    return _DwConv7.apply(x_nhwc, weight, bias)
+    return _DwConv7.apply(x_nhwc, weight, bias, False)
+
+
+def dwconv7_fork(x_nhwc, weight, bias):
+    """-> (conv(x), x): use the second output as the block's skip connection (see _DwConv7)."""
+    return _DwConv7.apply(x_nhwc, weight, bias, True)
 
 
 # --------------------------------------------------------------------------- layout

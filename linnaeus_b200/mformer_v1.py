@@ -104,12 +104,12 @@ class ConvNeXtBlock(nn.Module):
 
     def run(self, x: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
         C = x.shape[-1]
-        t = F.dwconv7(x.view(B, H, W, C), self.dwconv.weight, self.dwconv.bias)
+        t, skip = F.dwconv7_fork(x.view(B, H, W, C), self.dwconv.weight, self.dwconv.bias)
         t = F.layernorm(t.view(-1, C), self.norm.weight, self.norm.bias, 1e-6)
         mask = drop_path_mask(B, self.drop_prob, self.training, x.device)
         return F.mlp2(t, self.pwconv1.weight, self.pwconv1.bias, self.pwconv2.weight, self.pwconv2.bias,
                       w1c=_wc(self.pwconv1.weight), w2c=_wc(self.pwconv2.weight),
-                      act="gelu", residual=x, col_scale=self.gamma, row_scale=mask, rows_per_group=H * W)
+                      act="gelu", residual=skip.view(-1, C), col_scale=self.gamma, row_scale=mask, rows_per_group=H * W)
 
 
 class ConvNeXtDownsampleLayer(nn.Module):
@@ -168,13 +168,13 @@ class RoPE2DMHSABlock(nn.Module):
 
     def run(self, x: torch.Tensor, H: int, W: int) -> torch.Tensor:
         a = self.attn
-        t = F.layernorm(x, self.norm1.weight, self.norm1.bias, 1e-5)
+        t, x = F.layernorm_fork(x, self.norm1.weight, self.norm1.bias, 1e-5)  # x: skip connection (gradient fused into LN bwd)
         qkv = F.linear(t, a.qkv.weight, a.qkv.bias, weight_c=_wc(a.qkv.weight))
         o = F.rope_attention(qkv, a.freqs, H, W, a.num_heads, self.extra_token_num)
         B, N = x.shape[0], x.shape[1]
         m1 = drop_path_mask(B, self.drop_prob, self.training, x.device)
         x = F.linear(o, a.proj.weight, a.proj.bias, weight_c=_wc(a.proj.weight), residual=x, row_scale=m1, rows_per_group=N)
-        t = F.layernorm(x, self.norm2.weight, self.norm2.bias, 1e-5)
+        t, x = F.layernorm_fork(x, self.norm2.weight, self.norm2.bias, 1e-5)
         m2 = drop_path_mask(B, self.drop_prob, self.training, x.device)
         return F.mlp2(t, self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
                       w1c=_wc(self.mlp.fc1.weight), w2c=_wc(self.mlp.fc2.weight), act="gelu", residual=x,
@@ -325,6 +325,7 @@ class mFormerV1(nn.Module):
         self.dims, self.in_chans = dims, in_chans
         self._compute_dtype: torch.dtype | None = None  # None: follow autocast (on -> bf16, off -> fp32)
         self._shadow: _Bf16Shadow | None = None
+        self._side_stream = None  # metadata-token branch (see _extras_async)
 
     # -- init / metadata properties (mFormerV1.py:351-405) ---------------------
     def _init_weights(self, m):
@@ -408,9 +409,27 @@ class mFormerV1(nn.Module):
         finally:
             _ACTIVE_SHADOW = prev
 
+    def _extras_async(self, meta, cd):
+        """Both stages' metadata tokens on a side stream: ~40 tiny launches (3 components x 2 stages of
+        Linear -> ReLU -> LN -> ResNorm on [B, D]) that depend only on ``meta``, so they overlap the convolutional
+        trunk instead of sitting between its kernels.  autograd runs each backward node on its forward stream, so the
+        backward of this branch overlaps too; under CUDA-graph capture the fork / join become graph edges."""
+        if not (self.use_meta and meta is not None and self.meta_components):
+            return None, None, None
+        cur = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=meta.device)
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ex1 = self._extras(1, meta, cd)
+            ex2 = self._extras(2, meta, cd)
+        return ex1, ex2, side
+
     def _features(self, x, meta, cd):
         B, Cin, Hi, Wi = x.shape
         dims = self.dims
+        ex1, ex2, side = self._extras_async(meta, cd)
         # stem: 4x4/s4 conv as im2col (K = 48 padded to 64) + GEMM, then LN (NHWC rows)
         kpad = ((Cin * 16 + 63) // 64) * 64
         a = F.patchify(x, 4, kpad, cd)
@@ -429,7 +448,10 @@ class mFormerV1(nn.Module):
         H, W = H // 2, W // 2
 
         n_meta = self.extra_token_num - 1
-        ex1 = self._extras(1, meta, cd)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            for t in (ex1, ex2):
+                t.record_stream(torch.cuda.current_stream())
         if (ex1 is None) != (n_meta == 0):
             raise AssertionError(f"Input sequence length {H * W + 1 + (0 if ex1 is None else ex1.shape[1])} != H*W+extra {H * W + self.extra_token_num}")
         x3 = F.tokens_assemble(self.cls_token_1, ex1, y.view(B, H * W, dims[2]))
@@ -444,7 +466,6 @@ class mFormerV1(nn.Module):
             c1 = F.layernorm(c1, ln.weight, ln.bias, 1e-5)
         y = self.downsample_layers[2].run(patches.view(-1, dims[2]), B, H, W)
         H, W = H // 2, W // 2
-        ex2 = self._extras(2, meta, cd)
         x4 = F.tokens_assemble(self.cls_token_2, ex2, y.view(B, H * W, dims[3]))
         for blk in self.stages[3]:
             x4 = blk.run(x4, H, W)

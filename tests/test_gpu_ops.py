@@ -339,3 +339,37 @@ def test_aggregate_and_colsum():
     assert rel_err(w.grad.cpu(), wr.grad) < 1e-5 and rel_err(b.grad.cpu(), br.grad) < 1e-5
     x = torch.randn(1234, 77, device=DEV)
     assert rel_err(F.colsum(x), x.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fork_ops_fuse_the_skip_gradient(dtype):
+    """dwconv7_fork / layernorm_fork return (op(x), x); the gradient arriving on the second output must be added to
+    the op's input gradient inside the backward kernel (same result as autograd's separate add)."""
+    F = _F()
+    torch.manual_seed(3)
+    B, H, W, C = 2, 28, 28, 96
+    x0 = torch.randn(B, H, W, C, device=DEV).to(dtype)
+    w = (0.2 * torch.randn(C, 1, 7, 7, device=DEV)).requires_grad_(True)
+    b = (0.1 * torch.randn(C, device=DEV)).requires_grad_(True)
+    g1, g2 = torch.randn_like(x0), torch.randn_like(x0)
+    xa = x0.clone().requires_grad_(True)
+    y, skip = F.dwconv7_fork(xa, w, b)
+    (y * g1).sum().backward(retain_graph=True, inputs=[xa]) if False else torch.autograd.backward([y, skip], [g1, g2])
+    xb = x0.clone().requires_grad_(True)
+    yb = F.dwconv7(xb, w, b)
+    torch.autograd.backward([yb], [g1])
+    ref = xb.grad.float() + g2.float()
+    assert rel_err(y, yb) == 0.0
+    assert rel_err(xa.grad, ref) < tol(dtype)
+
+    lw = torch.randn(C, device=DEV, requires_grad=True)
+    lb = torch.randn(C, device=DEV, requires_grad=True)
+    xa = x0.view(-1, C).clone().requires_grad_(True)
+    y, skip = F.layernorm_fork(xa, lw, lb, 1e-6)
+    torch.autograd.backward([y, skip], [g1.view(-1, C), g2.view(-1, C)])
+    xb = x0.view(-1, C).clone().requires_grad_(True)
+    yb = F.layernorm(xb, lw, lb, 1e-6)
+    torch.autograd.backward([yb], [g1.view(-1, C)])
+    ref = xb.grad.float() + g2.view(-1, C).float()
+    assert rel_err(y, yb) == 0.0
+    assert rel_err(xa.grad, ref) < tol(dtype)

@@ -36,7 +36,7 @@ for (H, C) in ((56, 96), (28, 192)):
     db = torch.zeros(C, device=dev)
     nb = x.numel() * 2
     fma = x.numel() * 49
-    bench(f"dwconv7 fwd  {H}x{H}x{C}", lambda: call("lnx_dwconv7_fwd", x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, H, C, dt(x)), 2 * nb, flops=fma)
+    bench(f"dwconv7 fwd  {H}x{H}x{C}", lambda: call("lnx_dwconv7_fwd", x.data_ptr(), w.data_ptr(), bias.data_ptr(), None, y.data_ptr(), B, H, H, C, dt(x)), 2 * nb, flops=fma)
     bench(f"dwconv7 wgrad {H}x{H}x{C}", lambda: call("lnx_dwconv7_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H, H, C, dt(x)), 2 * nb, flops=fma)
 
 for (rows, C) in ((B * 3136, 96), (B * 784, 192), (B * 200, 384), (B * 53, 768)):
@@ -54,4 +54,4 @@ for (rows, C) in ((B * 3136, 96), (B * 784, 192), (B * 200, 384), (B * 53, 768))
     nb = rows * C * 2
     bench(f"layernorm fwd {rows}x{C}", lambda: call("lnx_layernorm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), None, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C, 1e-6, dt(x)), 2 * nb)
     bench(f"layernorm fwd+res {rows}x{C}", lambda: call("lnx_layernorm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), res.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C, 1e-6, dt(x)), 3 * nb)
-    bench(f"layernorm bwd {rows}x{C}", lambda: call("lnx_layernorm_bwd", g.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, C, dt(x)), 3 * nb)
+    bench(f"layernorm bwd {rows}x{C}", lambda: call("lnx_layernorm_bwd", g.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, C, dt(x)), 3 * nb)
