@@ -53,53 +53,40 @@ __global__ void rope_table_kernel(const float* __restrict__ freqs, float* __rest
   }
 }
 
-// one thread per 8 consecutive head-dim elements (4 pairs) of one (b, n, which, head)
-template <typename T>
+// CTA = TOK consecutive tokens; thread = (token, which in {q,k,v}, head, 8-element chunk): no per-element index
+// divisions, 16-byte coalesced reads of the [B*N, 3*heads*hd] rows, 128-byte segments on the head-major side.
+template <typename T, int TOK>
 __global__ void rope_qk_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ cos_tab, T* __restrict__ q, T* __restrict__ k,
-                                   T* __restrict__ v, int B, int N, int heads, int hd, int n_extra, float q_scale) {
+                                   T* __restrict__ v, long long BN, int N, int heads, int hd, int n_extra, float q_scale) {
   const int chunks = hd / 8;
-  const long long total = (long long)B * N * 3 * heads * chunks;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % chunks);
-    long long r = i / chunks;
-    const int h = (int)(r % heads); r /= heads;
-    const int which = (int)(r % 3); r /= 3;
-    const int n = (int)(r % N);
-    const long long b = r / N;
-    const T* src = qkv + i * 8;
-    float x[8];
-    if (sizeof(T) == 2) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(src);
-      const bf16* hh = reinterpret_cast<const bf16*>(&raw);
+  const int per_tok = 3 * heads * chunks;
+  const int t = threadIdx.x;
+  if (t >= per_tok * TOK) return;
+  const int tok = t / per_tok;
+  const int w = t - tok * per_tok;
+  const int ch = w % chunks;
+  const int h = (w / chunks) % heads;
+  const int which = w / (chunks * heads);
+  const long long row = (long long)blockIdx.x * TOK + tok;  // = b * N + n
+  if (row >= BN) return;
+  const long long b = row / N;
+  const int n = (int)(row - b * N);
+  float x[8];
+  ld8<T>(qkv + row * (long long)per_tok * 8 + (long long)w * 8, x);
+  if (which < 2) {
+    const float sc = (which == 0) ? q_scale : 1.0f;
+    if (n >= n_extra) {
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cos_tab + ((long long)(n - n_extra) * heads + h) * (hd / 2) + ch * 4));
+      const float ct[4] = {c4.x * sc, c4.y * sc, c4.z * sc, c4.w * sc};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = __bfloat162float(hh[e]);
+      for (int e = 0; e < 8; ++e) x[e] *= ct[e >> 1];
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = to_f32(src[e]);
-    }
-    if (which < 2) {
-      const float sc = (which == 0) ? q_scale : 1.0f;
-      if (n >= n_extra) {
-        const float* ct = cos_tab + ((long long)(n - n_extra) * heads + h) * (hd / 2) + ch * 4;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] *= ct[e >> 1] * sc;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] *= sc;
-      }
-    }
-    T* dst = (which == 0 ? q : which == 1 ? k : v) + (((b * heads + h) * N + n) * hd) + ch * 8;
-    if (sizeof(T) == 2) {
-      uint4 raw;
-      __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-      *reinterpret_cast<uint4*>(dst) = raw;
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dst[e] = from_f32<T>(x[e]);
+      for (int e = 0; e < 8; ++e) x[e] *= sc;
     }
   }
+  T* dst = (which == 0 ? q : which == 1 ? k : v) + (((b * heads + h) * N + n) * hd) + ch * 8;
+  st8<T>(dst, x);
 }
 
 // grid: (N, batch chunks); thread = (which in {q,k,v}, head, pair-chunk of 4 pairs)
@@ -126,6 +113,7 @@ __global__ void rope_qk_bwd_kernel(const T* __restrict__ dq, const T* __restrict
     const float sc = (which == 0) ? q_scale : 1.0f;
     float dth[4] = {0.f, 0.f, 0.f, 0.f};
     const T* gsrc = (which == 0 ? dq : which == 1 ? dk : dv);
+#pragma unroll 4
     for (int b = b0; b < b1; ++b) {
       const T* gp = gsrc + ((((long long)b * heads + h) * N + n) * hd) + ch * 8;
       const long long o = ((((long long)b * N + n) * 3 + which) * heads + h) * hd + ch * 8;
@@ -185,15 +173,20 @@ extern "C" int lnx_rope_qk_fwd(const void* qkv, const float* cos_tab, void* q, v
   LNX_REQUIRE(qkv && cos_tab && q && k && v, LNX_ERR_NULL);
   LNX_REQUIRE(B > 0 && N > n_extra && heads > 0 && hd % 8 == 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(lnx_aligned16(qkv) && lnx_aligned16(q) && lnx_aligned16(k) && lnx_aligned16(v), LNX_ERR_ALIGN);
-  const long long total = (long long)B * N * 3 * heads * (hd / 8);
-  const int blocks = (int)min((long long)kNumSMs * 16, (total + 255) / 256);
+  const int per_tok = 3 * heads * (hd / 8);
+  LNX_REQUIRE(per_tok <= 1024 && hd % 8 == 0 && (hd / 2) % 4 == 0, LNX_ERR_UNSUPPORTED);
+  const long long BN = (long long)B * N;
   cudaStream_t st = (cudaStream_t)s;
-  if (dtype == LNX_F32)
-    rope_qk_fwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)qkv, cos_tab, (float*)q, (float*)k, (float*)v, B, N, heads, hd, n_extra, q_scale);
-  else if (dtype == LNX_BF16)
-    rope_qk_fwd_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)qkv, cos_tab, (bf16*)q, (bf16*)k, (bf16*)v, B, N, heads, hd, n_extra, q_scale);
-  else
+#define LNX_ROPE_F(T, TOK)                                                                                                         \
+  rope_qk_fwd_kernel<T, TOK><<<(unsigned)((BN + TOK - 1) / TOK), ((per_tok * TOK + 31) / 32) * 32, 0, st>>>(                         \
+      (const T*)qkv, cos_tab, (T*)q, (T*)k, (T*)v, BN, N, heads, hd, n_extra, q_scale)
+  if (dtype == LNX_F32) {
+    if (per_tok * 4 <= 1024) LNX_ROPE_F(float, 4); else LNX_ROPE_F(float, 1);
+  } else if (dtype == LNX_BF16) {
+    if (per_tok * 4 <= 1024) LNX_ROPE_F(bf16, 4); else LNX_ROPE_F(bf16, 1);
+  } else
     return LNX_ERR_DTYPE;
+#undef LNX_ROPE_F
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
