@@ -38,7 +38,9 @@ enum {
   LNX_ERR_UNSUPPORTED = -5,
   LNX_ERR_NULL = -6
 };
-enum { LNX_ACT_NONE = 0, LNX_ACT_GELU = 1, LNX_ACT_RELU = 2 };
+/* LNX_ACT_GELU_DG: forward variant that stores gelu'(pre) (not pre) in aux_out, so the backward needs no
+ * transcendental: LNX_ACT_MUL multiplies the accumulator by act_grad_in (the stored derivative). */
+enum { LNX_ACT_NONE = 0, LNX_ACT_GELU = 1, LNX_ACT_RELU = 2, LNX_ACT_GELU_DG = 3, LNX_ACT_MUL = 4 };
 enum { LNX_LOSS_CE = 0, LNX_LOSS_LABEL_SMOOTHING = 1, LNX_LOSS_TAXONOMY = 2 };
 
 int lnx_version(void);

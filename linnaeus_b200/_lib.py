@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblinnaeus_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_DG, ACT_MUL = 0, 1, 2, 3, 4
 LOSS_CE, LOSS_LS, LOSS_TAXONOMY = 0, 1, 2
 
 P = c_void_p

@@ -182,6 +182,22 @@ __device__ __forceinline__ float2 gelu_grad_tanh3_x2(float2 x) {
   return __ffma2_rn(hn, sm1, __ffma2_rn(t, f2(0.5f), f2(0.5f)));
 }
 
+// gelu and its derivative from ONE tanh (forward epilogue that saves the derivative for the backward pass)
+__device__ __forceinline__ void gelu_both_tanh3_x2(float2 x, float2& gl, float2& dg) {
+  float2 x2 = __fmul2_rn(x, x);
+  x2.x = fminf(x2.x, 64.f);
+  x2.y = fminf(x2.y, 64.f);
+  const float2 p = __ffma2_rn(x2, __ffma2_rn(x2, f2(kGeluC2), f2(kGeluC1)), f2(kGeluC0));
+  const float2 dpn = __ffma2_rn(x2, __ffma2_rn(x2, f2(-2.5f * kGeluC2), f2(-1.5f * kGeluC1)), f2(-0.5f * kGeluC0));
+  const float2 u = __fmul2_rn(x, p);
+  const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 hx = __fmul2_rn(x, f2(0.5f));
+  gl = __ffma2_rn(hx, t, hx);
+  const float2 hn = __fmul2_rn(x, dpn);
+  const float2 sm1 = __ffma2_rn(t, t, f2(-1.0f));
+  dg = __ffma2_rn(hn, sm1, __ffma2_rn(t, f2(0.5f), f2(0.5f)));
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace lnx

@@ -26,13 +26,14 @@ __device__ __forceinline__ float gemm_epilogue_scalar(float v, int m, int n, lon
                                                       const TC* res) {
   using namespace lnx;
   if (g.bias) v += g.bias[n];
-  if (aux) aux[idx] = from_f32<TC>(v);
+  if (aux) aux[idx] = from_f32<TC>(g.act == LNX_ACT_GELU_DG ? gelu_grad_f(v) : v);
   if (agi) {
     const float u = to_f32(agi[idx]);
     if (g.act == LNX_ACT_GELU) v *= gelu_grad_f(u);
     else if (g.act == LNX_ACT_RELU) v = (u > 0.f) ? v : 0.f;
+    else if (g.act == LNX_ACT_MUL) v *= u;
   } else {
-    if (g.act == LNX_ACT_GELU) v = gelu_f(v);
+    if (g.act == LNX_ACT_GELU || g.act == LNX_ACT_GELU_DG) v = gelu_f(v);
     else if (g.act == LNX_ACT_RELU) v = fmaxf(v, 0.f);
   }
   if (g.col_scale) v *= g.col_scale[n];

@@ -263,7 +263,16 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
           vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
           vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
         }
-        if (aux) store8_from_f32<TC>(aux + idx, vv);
+        if (aux) {
+          if (g.act == LNX_ACT_GELU_DG) {
+            float dg[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dg[i] = gelu_grad_fast(vv[i]);
+            store8_from_f32<TC>(aux + idx, dg);
+          } else {
+            store8_from_f32<TC>(aux + idx, vv);
+          }
+        }
         if (agi) {
           float u[8];
           load8_as_f32<TC>(agi + idx, u);
@@ -273,8 +282,11 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
           } else if (g.act == LNX_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) vv[i] = u[i] > 0.f ? vv[i] : 0.f;
+          } else if (g.act == LNX_ACT_MUL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] *= u[i];
           }
-        } else if (g.act == LNX_ACT_GELU) {
+        } else if (g.act == LNX_ACT_GELU || g.act == LNX_ACT_GELU_DG) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) vv[i] = gelu_fast(vv[i]);
         } else if (g.act == LNX_ACT_RELU) {

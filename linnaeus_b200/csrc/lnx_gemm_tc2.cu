@@ -269,6 +269,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
               } else if (ACT == LNX_ACT_RELU) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) vv[k] = u[k] > 0.f ? vv[k] : 0.f;
+              } else if (ACT == LNX_ACT_MUL) {  // the saved tensor is the derivative itself
+#pragma unroll
+                for (int k = 0; k < 8; ++k) vv[k] *= u[k];
               }
             }
             if (SCALE) {
@@ -395,7 +398,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
                 vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
               }
-              if (AUX) *reinterpret_cast<uint4*>(st1 + soff) = pack8(vv);
+              if (AUX && ACT == LNX_ACT_GELU_DG) {  // out = gelu(pre), aux = gelu'(pre): one tanh for both
+                float dg[8];
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                  float2 gl, d;
+                  gelu_both_tanh3_x2(make_float2(vv[i], vv[i + 1]), gl, d);
+                  vv[i] = gl.x; vv[i + 1] = gl.y;
+                  dg[i] = d.x; dg[i + 1] = d.y;
+                }
+                *reinterpret_cast<uint4*>(st1 + soff) = pack8(dg);
+              } else if (AUX) {
+                *reinterpret_cast<uint4*>(st1 + soff) = pack8(vv);
+              }
               if (IN_KIND == 2) {
                 float u[8];
                 unpack8(*reinterpret_cast<const uint4*>(st1 + soff), u);
@@ -646,6 +661,12 @@ int lnx_gemm_tc2(const GemmArgs& g, float* colsum_out, cudaStream_t st) {
     case LNX_ACT_NONE: return launch_none(L, in_kind, aux, scale, colsum);
     case LNX_ACT_GELU: return launch_act<LNX_ACT_GELU>(L, in_kind, aux, scale, colsum);
     case LNX_ACT_RELU: return launch_act<LNX_ACT_RELU>(L, in_kind, aux, scale, colsum);
+    case LNX_ACT_GELU_DG:
+      if (!aux || in_kind || scale || colsum) return LNX_ERR_UNSUPPORTED;
+      return launch_variant<LNX_ACT_GELU_DG, 0, true, false, false>(L);
+    case LNX_ACT_MUL:
+      if (in_kind != 2 || aux || scale) return LNX_ERR_UNSUPPORTED;
+      return colsum ? launch_variant<LNX_ACT_MUL, 2, false, false, true>(L) : launch_variant<LNX_ACT_MUL, 2, false, false, false>(L);
   }
   return LNX_ERR_UNSUPPORTED;
 }

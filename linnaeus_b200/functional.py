@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, call, dt, ptr
+from ._lib import ACT_GELU, ACT_GELU_DG, ACT_MUL, ACT_NONE, ACT_RELU, call, dt, ptr
 
 # set by tests to force the CUDA-core kernels instead of tcgen05 ones
 FORCE_SIMT = False
@@ -215,8 +215,11 @@ class _Mlp2(torch.autograd.Function):
         w1c = w1c if w1c is not None else compute_copy(w1, x2.dtype)
         w2c = w2c if w2c is not None else compute_copy(w2, x2.dtype)
         need_grad = any(ctx.needs_input_grad)
+        # GELU: the forward epilogue stores gelu'(pre) (one tanh serves both), so the backward epilogue is a multiply
         pre = torch.empty((M, Hd), dtype=x2.dtype, device=x2.device) if need_grad else None
-        h = gemm(x2, w1c, M, Hd, K, bias=b1, act=act, aux_out=pre)
+        save_dg = need_grad and act == ACT_GELU
+        h = gemm(x2, w1c, M, Hd, K, bias=b1, act=ACT_GELU_DG if save_dg else act, aux_out=pre)
+        ctx.save_dg = save_dg
         res2 = _c(residual).view(M, N) if residual is not None else None
         y = gemm(h, w2c, M, N, Hd, bias=b2, residual=res2, col_scale=col_scale, row_scale=row_scale, rows_per_group=rpg)
         ctx.save_for_backward(x2, w1c, w2c, pre, h, col_scale, w2, b2, row_scale)
@@ -243,7 +246,7 @@ class _Mlp2(torch.autograd.Function):
         p_w1, p_b1, p_w2, p_b2, p_cs = ctx.params
         s_w1, s_b1, s_w2, s_b2 = _sink(p_w1), _sink(p_b1), _sink(p_w2), _sink(p_b2)
         db1 = s_b1 if s_b1 is not None else torch.zeros(Hd, dtype=torch.float32, device=dy2.device)
-        dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=act, act_grad_in=pre)
+        dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=ACT_MUL if ctx.save_dg else act, act_grad_in=pre)
         d_cs = dw2 = db2 = None
         if col_scale is not None:
             db2_raw = torch.zeros(N, dtype=torch.float32, device=dy2.device)
