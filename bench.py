@@ -26,6 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FWD_GFLOP = {"sm": 8.659, "md": 12.505, "xl": 448.16}  # per image (SURVEY.md section 6, 224^2; xl at 384^2)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (profiles/r01_kernels_summary.md),
+# keyed by (variant, per-GPU batch, image size, dtype); None when that exact shape was not captured
+NCU_TRAFFIC_BYTES = {}
 
 
 def parse():
@@ -267,8 +270,10 @@ def run_b200(args):
     if use_graph:
         launches = ts.launches_per_step * args.steps if hasattr(ts, "launches_per_step") else launches
 
-    # roofline of the dominant kernel, timed live: the stage-0 pointwise-expand GEMM (+bias+GELU, pre-activation
-    # saved) of the ConvNeXt blocks -- tcgen05 GEMM, HBM bound (K = 96): bytes = A + W + 2 outputs
+    # roofline of the dominant kernel, timed live: the stage-0 pointwise-expand GEMM of the ConvNeXt blocks exactly as the
+    # training step launches it (gemm_tc2_kernel<GELU_DG, aux>: bias + GELU, gelu'(pre) saved as second output).  K = 96:
+    # HBM bound, algorithmic bytes = A + W + 2 outputs.  `traffic` = dram bytes per launch of this kernel from the ncu
+    # --set full capture committed under profiles/ (B = 256 shape only).
     import linnaeus_b200.functional as F
     M, K, N = B * (S // 4) ** 2, cfg.MODEL.CONVNEXT_STAGES.DIMS[0], 4 * cfg.MODEL.CONVNEXT_STAGES.DIMS[0]
     esz = 2 if cd == torch.bfloat16 else 4
@@ -277,13 +282,14 @@ def run_b200(args):
     b_ = torch.randn(N, device=dev)
     o_, aux_ = torch.empty(M, N, device=dev, dtype=cd), torch.empty(M, N, device=dev, dtype=cd)
     def gemm():
-        F.gemm(a_, w_, M, N, K, out=o_, bias=b_, act=1, aux_out=aux_)
+        F.gemm(a_, w_, M, N, K, out=o_, bias=b_, act=3, aux_out=aux_)
     kms, _ = timed(gemm, 20, 3)
     alg_bytes = (M * K + N * K + 2 * M * N) * esz
     ach = alg_bytes / (kms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gemm_tc_kernel (pwconv1 stage 0: M=%d K=%d N=%d, bias+GELU, 2 outputs)" % (M, K, N),
-                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": peak_src,
-                "ms_per_launch": kms,
+    traffic = NCU_TRAFFIC_BYTES.get((args.variant, B, S, args.dtype))
+    roofline = {"bound": "hbm", "kernel": "gemm_tc2_kernel<GELU_DG, aux> (pwconv1 stage 0: M=%d K=%d N=%d, bias+GELU, saves gelu')" % (M, K, N),
+                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes": alg_bytes, "ms_per_launch": kms,
                 "model_tflops": value * FWD_GFLOP.get(args.variant, 0.0) * flop_mult / 1e3,
                 "model_frac_of_bf16_sustained": value * FWD_GFLOP.get(args.variant, 0.0) * flop_mult / 1e3 / tf_sus}
 

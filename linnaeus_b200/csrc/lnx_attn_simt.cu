@@ -299,6 +299,7 @@ int lnx_attn_bwd_tc(const void* q, const void* k, const void* v, const void* out
                     void* dk, void* dv, int B, int heads, int N, int hd, cudaStream_t st);
 
 int lnx_attn_fwd_tc2(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd, cudaStream_t st);
+int lnx_attn_fwd_long_tc2(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd, cudaStream_t st);
 int lnx_attn_bwd_tc2(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, void* dq, void* dk,
                      void* dv, int B, int heads, int N, int hd, cudaStream_t st);
 
@@ -309,6 +310,8 @@ extern "C" int lnx_attn_fwd(const void* q, const void* k, const void* v, void* o
   LNX_REQUIRE(lnx_aligned16(q) && lnx_aligned16(k) && lnx_aligned16(v) && lnx_aligned16(out), LNX_ERR_ALIGN);
   if (dtype == LNX_BF16 && !force_simt) {
     int r = lnx_attn_fwd_tc2(q, k, v, out, lse, B, heads, N, hd, (cudaStream_t)s);  // persistent, pipelined (N <= 240)
+    if (r != LNX_ERR_UNSUPPORTED) return r;
+    r = lnx_attn_fwd_long_tc2(q, k, v, out, lse, B, heads, N, hd, (cudaStream_t)s);  // streamed key tiles, online softmax
     if (r != LNX_ERR_UNSUPPORTED) return r;
     r = lnx_attn_fwd_tc(q, k, v, out, lse, B, heads, N, hd, (cudaStream_t)s);
     if (r != LNX_ERR_UNSUPPORTED) return r;

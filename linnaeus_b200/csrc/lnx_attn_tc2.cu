@@ -247,6 +247,232 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
   }
 }
 
+// ------------------------------------------------------------------ forward, long sequences (N > 240)
+// Same roles as above, but the keys are streamed in tiles of 128 with an online softmax: an item is one
+// (problem, query tile, key tile).  The softmax warps keep the running row max / row sum in registers and publish the
+// rescale factor alpha = exp(m_old - m_new) of every item; the output warps own the fp32 output accumulator in
+// REGISTERS (O = O * alpha + P_j V_j, P_j V_j read from TMEM after each non-accumulating MMA), so TMEM is never
+// written by threads.  K/V tiles come through a 3-deep ring (re-read per query tile: they hit in L2).
+struct LongParams {
+  int B, heads, N;
+  int n_qt, n_kt, n_bh;
+};
+constexpr int KT = 128;
+constexpr int L_KV_STAGES = 3;
+enum { L_KV_FULL = 0, L_KV_EMPTY = 3, L_Q_FULL = 6, L_Q_EMPTY = 8, L_S_FULL = 10, L_O_FULL = 12, L_T_EMPTY = 14, L_P_FULL = 16, L_P_EMPTY = 17, L_NBARS = 18 };
+
+__global__ void __launch_bounds__(448, 1) attn_fwd_long_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out,
+                                                                    float* __restrict__ lse, const LongParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sKV = base;                               // [3]{K tile, V tile} of [128][64]
+  unsigned char* sQ = sKV + L_KV_STAGES * 32768;           // [2][128][64]
+  unsigned char* sP = sQ + 2 * 16384;                      // 2 blocks of [128][64]
+  float* sMax = reinterpret_cast<float*>(sP + 32768);      // [2 halves][128]  (per item, exchanged inside the softmax warps)
+  float* sAlpha = sMax + 256;                              // [2 TMEM buffers][128]  rescale factor of the item
+  float* sFin = sAlpha + 256;                              // [2 buffers][3][128]: final max, row sum of half 0 / half 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sFin + 768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L_NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = p.n_bh * p.n_qt;  // (problem, query tile)
+  const int my_units = ((int)blockIdx.x < n_units) ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int T = my_units * p.n_kt;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    for (int i = 0; i < L_KV_STAGES; ++i) {
+      mbar_init(&bars[L_KV_FULL + i], 1);
+      mbar_init(&bars[L_KV_EMPTY + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[L_Q_FULL + i], 1);
+      mbar_init(&bars[L_Q_EMPTY + i], 1);
+      mbar_init(&bars[L_S_FULL + i], 1);
+      mbar_init(&bars[L_O_FULL + i], 1);
+      mbar_init(&bars[L_T_EMPTY + i], 128);
+    }
+    mbar_init(&bars[L_P_FULL], 256);
+    mbar_init(&bars[L_P_EMPTY], 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int t = 0;
+      for (int u = 0; u < my_units; ++u) {
+        const int unit = (int)blockIdx.x + u * (int)gridDim.x;
+        const int bh = unit / p.n_qt, qt = unit - bh * p.n_qt;
+        const int qs = u & 1;
+        mbar_wait_relaxed(&bars[L_Q_EMPTY + qs], (((uint32_t)u >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&bars[L_Q_FULL + qs], 16384);
+        tma_load_3d(sQ + qs * 16384, &tmQ, &bars[L_Q_FULL + qs], 0, qt * QT, bh);
+        for (int j = 0; j < p.n_kt; ++j, ++t) {
+          const int ks = t % L_KV_STAGES;
+          mbar_wait_relaxed(&bars[L_KV_EMPTY + ks], (((uint32_t)(t / L_KV_STAGES)) & 1u) ^ 1u);
+          mbar_expect_tx(&bars[L_KV_FULL + ks], 32768);
+          tma_load_3d(sKV + ks * 32768, &tmK, &bars[L_KV_FULL + ks], 0, j * KT, bh);
+          tma_load_3d(sKV + ks * 32768 + 16384, &tmV, &bars[L_KV_FULL + ks], 0, j * KT, bh);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(QT, KT, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(QT, HD, 0, 1);
+      const uint32_t aP = smem_u32(sP);
+      auto issue_s = [&](int t) {
+        const int u = t / p.n_kt, j = t - u * p.n_kt;
+        const int ks = t % L_KV_STAGES, qs = u & 1, buf = t & 1;
+        if (j == 0) mbar_wait(&bars[L_Q_FULL + qs], ((uint32_t)u >> 1) & 1u);
+        mbar_wait(&bars[L_KV_FULL + ks], ((uint32_t)(t / L_KV_STAGES)) & 1u);
+        mbar_wait(&bars[L_T_EMPTY + buf], (((uint32_t)t >> 1) & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t aq = smem_u32(sQ + qs * 16384), ak = smem_u32(sKV + ks * 32768);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem + buf * 256, make_smem_desc(aq + k * 32, 0, 1024), make_smem_desc(ak + k * 32, 0, 1024), idesc_s, k > 0);
+        umma_commit(&bars[L_S_FULL + buf]);
+        if (j == p.n_kt - 1) umma_commit(&bars[L_Q_EMPTY + qs]);
+      };
+      if (T > 0) issue_s(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_s(t + 1);
+        const int ks = t % L_KV_STAGES, buf = t & 1;
+        mbar_wait(&bars[L_P_FULL], (uint32_t)t & 1u);
+        tcgen05_fence_after();
+        const uint32_t av = smem_u32(sKV + ks * 32768 + 16384);
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k)
+          umma_bf16(tmem + buf * 256, make_smem_desc(aP + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024), make_smem_desc(av + k * 2048, 0, 1024),
+                    idesc_o, k > 0);
+        umma_commit(&bars[L_O_FULL + buf]);
+        umma_commit(&bars[L_P_EMPTY]);
+        umma_commit(&bars[L_KV_EMPTY + ks]);
+      }
+    }
+  } else if (warp < 10) {
+    // ===================== softmax: two threads per query row, 64 keys of the tile each =====================
+    const int sw = warp - 2;
+    const int q = warp & 3;
+    const int half = sw >> 2;
+    const int r = q * 32 + lane;
+    float m_run = -INFINITY, l_run = 0.f;  // running max (shared by both halves), running sum of this half
+    for (int t = 0; t < T; ++t) {
+      const int u = t / p.n_kt, j = t - u * p.n_kt;
+      const int buf = t & 1;
+      const uint32_t trow = tmem + buf * 256 + ((uint32_t)(q * 32) << 16);
+      const int key0 = j * KT + half * 64;
+      if (j == 0) {
+        m_run = -INFINITY;
+        l_run = 0.f;
+      }
+      mbar_wait(&bars[L_S_FULL + buf], ((uint32_t)t >> 1) & 1u);
+      tcgen05_fence_after();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[16];
+        tmem_ld16(trow + half * 64 + cc * 16, v);
+        const int kb = key0 + cc * 16;
+        if (kb + 16 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (kb + i < p.N) mx = fmaxf(mx, v[i]);
+        }
+      }
+      sMax[half * 128 + r] = mx;
+      named_bar(1, 256);
+      mx = fmaxf(mx, sMax[(half ^ 1) * 128 + r]);
+      const float m_new = fmaxf(m_run, mx);  // finite: key tile 0 always holds valid keys
+      const float alpha = ex2f((m_run - m_new) * LOG2E);  // 0 on the first tile (m_run = -inf)
+      m_run = m_new;
+      const float mxl = m_new * LOG2E;
+      mbar_wait(&bars[L_P_EMPTY], ((uint32_t)t & 1u) ^ 1u);
+      float sum = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[16];
+        tmem_ld16(trow + half * 64 + cc * 16, v);
+        const int kb = key0 + cc * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float e = ex2f(fmaf(v[i], LOG2E, -mxl));
+          if (kb + 16 > p.N && kb + i >= p.N) e = 0.f;
+          sum += e;
+          v[i] = e;
+        }
+        store16_sw(sP, r, half * 64 + cc * 16, v);
+      }
+      l_run = fmaf(l_run, alpha, sum);
+      if (half == 0) sAlpha[buf * 128 + r] = alpha;
+      if (j == p.n_kt - 1) {
+        if (half == 0) sFin[buf * 384 + r] = m_run;
+        sFin[buf * 384 + 128 + half * 128 + r] = l_run;
+      }
+      fence_proxy_async_smem();
+      tcgen05_fence_before();
+      mbar_arrive(&bars[L_P_FULL]);
+      named_bar(2, 256);  // sMax is rewritten by the next item
+    }
+  } else {
+    // ===================== output: one thread per query row, fp32 accumulator in registers =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    float acc[HD];
+    for (int t = 0; t < T; ++t) {
+      const int u = t / p.n_kt, j = t - u * p.n_kt;
+      const int buf = t & 1;
+      const uint32_t trow = tmem + buf * 256 + ((uint32_t)(q * 32) << 16);
+      mbar_wait(&bars[L_O_FULL + buf], ((uint32_t)t >> 1) & 1u);
+      tcgen05_fence_after();
+      const float alpha = (j == 0) ? 0.f : sAlpha[buf * 128 + r];
+#pragma unroll
+      for (int c = 0; c < HD; c += 16) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16(trow + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c + i] = (j == 0) ? v[i] : fmaf(acc[c + i], alpha, v[i]);
+      }
+      if (j == p.n_kt - 1) {
+        const int unit = (int)blockIdx.x + u * (int)gridDim.x;
+        const int bh = unit / p.n_qt, qt = unit - bh * p.n_qt;
+        const int m = qt * QT + r;
+        const float mx = sFin[buf * 384 + r];
+        const float sum = sFin[buf * 384 + 128 + r] + sFin[buf * 384 + 256 + r];
+        const float inv = 1.0f / sum;
+        const int b = bh / p.heads, h = bh - b * p.heads;
+        if (m < p.N) {
+          bf16* dst = out + (((long long)b * p.N + m) * p.heads + h) * HD;
+#pragma unroll
+          for (int c = 0; c < HD; c += 8)
+            *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack2(acc[c] * inv, acc[c + 1] * inv), pack2(acc[c + 2] * inv, acc[c + 3] * inv),
+                                                            pack2(acc[c + 4] * inv, acc[c + 5] * inv), pack2(acc[c + 6] * inv, acc[c + 7] * inv));
+          lse[(long long)bh * p.N + m] = mx + __logf(sum);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&bars[L_T_EMPTY + buf]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
 // ------------------------------------------------------------------ backward
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ tile 0 [384,448) | dQ tile 1 [448,512)
 struct BwdParams {
@@ -475,6 +701,27 @@ int lnx_attn_fwd_tc2(const void* q, const void* k, const void* v, void* out, flo
     smem_set = (int)smem;
   }
   attn_fwd_tc2_kernel<<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tq, tk, tv, (bf16*)out, lse, p);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+int lnx_attn_fwd_long_tc2(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd, cudaStream_t st) {
+  if (hd != HD || N < 1) return LNX_ERR_UNSUPPORTED;
+  LongParams p;
+  p.B = B; p.heads = heads; p.N = N;
+  p.n_qt = (N + QT - 1) / QT;
+  p.n_kt = (N + KT - 1) / KT;
+  p.n_bh = B * heads;
+  CUtensorMap tq, tk, tv;
+  if (!head_tmap(&tq, q, p.n_bh, N, QT) || !head_tmap(&tk, k, p.n_bh, N, KT) || !head_tmap(&tv, v, p.n_bh, N, KT)) return LNX_ERR_UNSUPPORTED;
+  const size_t smem = 1024 + L_KV_STAGES * 32768 + 2 * 16384 + 32768 + (256 + 256 + 768) * 4 + L_NBARS * 8 + 64;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_long_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return lnx_set_cuda_error(e);
+    attr = true;
+  }
+  attn_fwd_long_tc2_kernel<<<min(p.n_bh * p.n_qt, kNumSMs), 448, smem, st>>>(tq, tk, tv, (bf16*)out, lse, p);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }

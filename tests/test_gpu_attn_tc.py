@@ -17,7 +17,8 @@ def _ref(q, k, v):
     return att @ v.float(), att
 
 
-@pytest.mark.parametrize("B,heads,N", [(2, 6, 200), (3, 12, 53), (1, 2, 256), (2, 3, 128), (1, 4, 17), (1, 2, 129), (1, 1, 64)])
+@pytest.mark.parametrize("B,heads,N", [(2, 6, 200), (3, 12, 53), (1, 2, 256), (2, 3, 128), (1, 4, 17), (1, 2, 129), (1, 1, 64), (1, 2, 300), (2, 3, 580),
+                                        (1, 2, 1000), (1, 1, 241)])
 def test_attn_tc_forward_backward(B, heads, N):
     from linnaeus_b200._lib import call
 

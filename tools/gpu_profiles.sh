@@ -1,8 +1,11 @@
 #!/bin/bash
-# Round profile pass: plain bench, ncu launch list of the same command, ncu --set full of the top kernels.
+# Round profile pass: plain bench, ncu launch list of the same command, ncu --set full of every hot kernel.
+# Only text summaries are kept (gpurun_out/ is capped at 64 MiB): the .ncu-rep is converted to CSV on the box and removed.
 mkdir -p gpurun_out
+rm -f gpurun_out/*.ncu-rep
 timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_prof_plain.log 2>&1; echo "plain rc $?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "launch list rc $?"
-timeout 600 python tools/prof_gemm.py 256 > gpurun_out/prof_gemm.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc2_kernel" -s 6 -c 2 -o gpurun_out/r01_gemm_pw1 -f python tools/prof_gemm.py 256 > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm rc $?"
-wc -l gpurun_out/r01_launches.csv
+timeout 300 python tools/prof_kernels.py 256 3 gpurun_out/r01_kernel_table.md > gpurun_out/prof_kernels.log 2>&1; echo "kernels rc $?"
+timeout 1200 ncu --set full --clock-control none -k regex:"gemm_tc2|wgrad_tc|dwconv7|ln_fwd_bf16|ln_bwd_bf16|attn_fwd_tc2|attn_bwd_tc2|rope_qk" -o /tmp/r01_kernels -f python tools/prof_kernels.py 256 1 > gpurun_out/ncu_kernels.log 2>&1; echo "ncu kernels rc $?"
+ncu -i /tmp/r01_kernels.ncu-rep --page raw --csv > gpurun_out/r01_kernels_raw.csv 2>/dev/null; ls -la gpurun_out/r01_kernels_raw.csv
+du -sh gpurun_out
