@@ -327,3 +327,51 @@ def make_synthetic_config(
         c.MODEL.EXTRA_TOKEN_NUM = 1 + len(SYNTH_META)
     c.TRAIN.GRADIENT_CHECKPOINTING.ENABLED_NORMAL_STEPS = False
     return c, num_classes
+
+
+# ---------------------------------------------------------------------------
+# mFormerV0 (config 5): arch table mirrored from configs/model/archs/mFormerV0/*.yaml
+# ---------------------------------------------------------------------------
+_ARCH_V0 = {
+    #       stem  conv embed   conv out     conv depths  conv strides              attn dims     attn depths  heads
+    "sm": (64, [64, 96], [96, 192], [2, 3], [[2, 1], [1, 1, 1]], [384, 768], [5, 2], [8, 8]),
+}
+
+
+def make_synthetic_config_v0(variant: str = "sm", img_size: int = 224, n_tasks: int = 6, meta: bool = True, conv_embed=None, conv_out=None,
+                             conv_depths=None, conv_strides=None, attn_dims=None, attn_depths=None, heads=None) -> tuple[CfgNode, dict[str, int]]:
+    """Synthetic mFormerV0 configuration: RelativeAttention variant, same synthetic heads /
+    metadata components as the V1 benchmark.  Returns ``(cfg, num_classes)``."""
+    stem, ce, co, cd, cstr, ad, adep, hd = _ARCH_V0[variant]
+    ce = list(conv_embed) if conv_embed is not None else ce
+    co = list(conv_out) if conv_out is not None else co
+    cd = list(conv_depths) if conv_depths is not None else cd
+    cstr = [list(s) for s in conv_strides] if conv_strides is not None else cstr
+    ad = list(attn_dims) if attn_dims is not None else ad
+    adep = list(attn_depths) if attn_depths is not None else adep
+    hd = list(heads) if heads is not None else hd
+    c = get_default_config()
+    c.MODEL.TYPE = "mFormerV0"
+    c.MODEL.NAME = f"mFormerV0_{variant}"
+    c.MODEL.IMG_SIZE = img_size
+    c.DATA.IMG_SIZE = img_size
+    c.MODEL.DROP_PATH_RATE = 0.0
+    c.MODEL.DROP_RATE = 0.0
+    c.MODEL.ATTN_DROP_RATE = 0.0
+    c.MODEL.CONV_STAGES = CfgNode({"STEM_OUT": ce[0], "EMBED_DIMS": ce, "OUT_CHANNELS": co, "DEPTHS": cd, "STRIDE_SEQS": cstr}, new_allowed=True)
+    c.MODEL.ATTENTION_STAGES = CfgNode(
+        {"EMBED_DIMS": ad, "DEPTHS": adep, "NUM_HEADS": hd, "MLP_RATIO": [4.0, 4.0],
+         "ATTENTION_TYPE": ["RelativeAttention", "RelativeAttention"],
+         "STRIDE_SEQS": [[2] + [1] * (adep[0] - 1), [2] + [1] * (adep[1] - 1)]}, new_allowed=True)
+    tasks = SYNTH_TASKS[:n_tasks]
+    c.DATA.TASK_KEYS_H5 = list(tasks)
+    num_classes = dict(zip(tasks, SYNTH_CLASSES[:n_tasks]))
+    for t in tasks:
+        c.MODEL.CLASSIFICATION.HEADS[t] = CfgNode({"TYPE": "Linear"}, new_allowed=True)
+    c.DATA.META.ACTIVE = bool(meta)
+    if meta:
+        for name, dim, idx in SYNTH_META:
+            c.DATA.META.COMPONENTS[name] = CfgNode({"ENABLED": True, "DIM": dim, "IDX": idx}, new_allowed=True)
+        c.MODEL.EXTRA_TOKEN_NUM = 1 + len(SYNTH_META)
+    c.TRAIN.GRADIENT_CHECKPOINTING.ENABLED_NORMAL_STEPS = False
+    return c, num_classes

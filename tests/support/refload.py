@@ -94,3 +94,38 @@ def synthetic_taxonomy_tree(num_classes: dict):
         cp = num_classes[hi]
         hmap[lo] = {i: (0 if i == 0 else 1 + (i - 1) % (cp - 1)) for i in range(num_classes[lo])}
     return TaxonomyTree(hmap, tasks, num_classes)
+
+
+def reference_config_v0(img_size: int = 224, n_tasks: int = 6, meta: bool = True, **arch_kw):
+    """Reference default config + the mFormerV0 arch section produced by linnaeus_b200.config.make_synthetic_config_v0
+    (same values as configs/model/archs/mFormerV0/mFormerV0_sm.yaml), with the deterministic eval settings."""
+    import_reference()
+    from linnaeus.config import get_default_config
+    from yacs.config import CfgNode as CN
+    from linnaeus_b200.config import SYNTH_CLASSES, SYNTH_META, SYNTH_TASKS, make_synthetic_config_v0
+
+    mine, _ = make_synthetic_config_v0("sm", img_size, n_tasks, meta, **arch_kw)
+    cfg = get_default_config()
+    cfg.defrost()
+    cfg.MODEL.TYPE = "mFormerV0"
+    cfg.MODEL.IMG_SIZE = img_size
+    cfg.MODEL.DROP_PATH_RATE = 0.0
+    cfg.MODEL.DROP_RATE = 0.0
+    cfg.MODEL.ATTN_DROP_RATE = 0.0
+    cfg.MODEL.PRETRAINED = None
+    cfg.MODEL.ONLY_LAST_CLS = False
+    cfg.MODEL.CONV_STAGES = CN({k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in mine.MODEL.CONV_STAGES.items()}, new_allowed=True)
+    cfg.MODEL.ATTENTION_STAGES = CN({k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in mine.MODEL.ATTENTION_STAGES.items()},
+                                    new_allowed=True)
+    tasks = SYNTH_TASKS[:n_tasks]
+    cfg.DATA.TASK_KEYS_H5 = list(tasks)
+    cfg.MODEL.CLASSIFICATION.HEADS = CN(new_allowed=True)
+    for t in tasks:
+        cfg.MODEL.CLASSIFICATION.HEADS[t] = CN({"TYPE": "Linear"}, new_allowed=True)
+    cfg.DATA.META.ACTIVE = bool(meta)
+    cfg.DATA.META.COMPONENTS = CN(new_allowed=True)
+    if meta:
+        for name, dim, idx in SYNTH_META:
+            cfg.DATA.META.COMPONENTS[name] = CN({"ENABLED": True, "DIM": dim, "IDX": idx}, new_allowed=True)
+    cfg.TRAIN.GRADIENT_CHECKPOINTING.ENABLED_NORMAL_STEPS = False
+    return cfg, dict(zip(tasks, SYNTH_CLASSES[:n_tasks]))
