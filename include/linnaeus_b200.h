@@ -40,7 +40,7 @@ enum {
 };
 /* LNX_ACT_GELU_DG: forward variant that stores gelu'(pre) (not pre) in aux_out, so the backward needs no
  * transcendental: LNX_ACT_MUL multiplies the accumulator by act_grad_in (the stored derivative). */
-enum { LNX_ACT_NONE = 0, LNX_ACT_GELU = 1, LNX_ACT_RELU = 2, LNX_ACT_GELU_DG = 3, LNX_ACT_MUL = 4 };
+enum { LNX_ACT_NONE = 0, LNX_ACT_GELU = 1, LNX_ACT_RELU = 2, LNX_ACT_GELU_DG = 3, LNX_ACT_MUL = 4, LNX_ACT_SWISH = 5 };
 enum { LNX_LOSS_CE = 0, LNX_LOSS_LABEL_SMOOTHING = 1, LNX_LOSS_TAXONOMY = 2 };
 
 int lnx_version(void);
@@ -190,6 +190,26 @@ int lnx_clip_coef(const float* sumsq, float gscale, float clip, float* norm_out,
 int lnx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
               float weight_decay, float bias_corr1, float bias_corr2, float gscale, const float* coef,
               const float* lr_dev, const float* step_dev, lnx_stream_t s);
+
+/* ---- mFormerV0 (RelativeAttention variant) inference --------------------- */
+/* Gather for dense 3x3 convs (pad 1): out[b*Ho*Wo + ho*Wo + wo, (kh*3+kw)*C + c] = x[b, ho*stride-1+kh, wo*stride-1+kw, c]
+ * (zero outside).  x is NHWC in `dtype` (Kpad = 9C), or the fp32 NCHW input image when x_is_nchw_f32 (any C, columns
+ * zero padded to Kpad).  Input side of nn.Conv2d(k=3) of the stem (R/models/mFormerV0.py:166-190) and of
+ * OverlapPatchEmbed.proj (R/models/blocks/relative_mhsa.py:57-66); the contraction runs on lnx_gemm. */
+int lnx_im2col3x3(const void* x, int x_is_nchw_f32, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo, int Kpad, int dtype,
+                  lnx_stream_t s);
+/* nn.MaxPool2d(3, 2, 1) on NHWC (R/models/mFormerV0.py:193). */
+int lnx_maxpool3s2(const void* x, void* y, int B, int H, int W, int C, int dtype, lnx_stream_t s);
+/* Depthwise 3x3 with explicit top/left padding (TF "same" static padding of Conv2dStaticSamePadding,
+ * R/models/blocks/mb_conv.py:46-99), y = act(conv(x) * scale[c] + shift[c]) (folded BatchNorm; act 1 = swish), and
+ * pool_sum[b, c] += sum over pixels of y (nullable; the squeeze-excite average pool, mb_conv.py:239). */
+int lnx_dwconv3_fwd(const void* x, const float* w9c, const float* scale, const float* shift, void* y, float* pool_sum, int B, int H, int W,
+                    int C, int stride, int pad_t, int pad_l, int Ho, int Wo, int act, int dtype, lnx_stream_t s);
+/* y[b, p, c] = x[b, p, c] * sigmoid(gate[b, c])  (squeeze-excite gating, mb_conv.py:242). */
+int lnx_se_scale(const void* x, const float* gate, void* y, int B, int HW, int C, int dtype, lnx_stream_t s);
+/* out[b, n, h*hd + d] = softmax_j(scale * q k^T + bias[h, n, j]) v with q/k/v read from qkv [B, N, 3, heads, hd]
+ * (RelativeAttention.forward, R/models/blocks/relative_mhsa.py:201-236); bias float [heads, N, N] or NULL. */
+int lnx_attn_bias_fwd(const void* qkv, const float* bias, void* out, int B, int heads, int N, int hd, float scale, int dtype, lnx_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblinnaeus_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_DG, ACT_MUL = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_DG, ACT_MUL, ACT_SWISH = 0, 1, 2, 3, 4, 5
 LOSS_CE, LOSS_LS, LOSS_TAXONOMY = 0, 1, 2
 
 P = c_void_p
@@ -40,6 +40,11 @@ SIGNATURES = {
     "lnx_dwconv7_wgrad": [P, P, P, P, I, I, I, I, I, P],
     "lnx_gemm": [I, P, L, I, P, L, I, P, I, I, I, I, P, I, P, P, P, P, P, I, P, I, I, P],
     "lnx_wgrad": [P, L, P, L, P, P, L, I, I, I, P],
+    "lnx_im2col3x3": [P, I, P, I, I, I, I, I, I, I, I, I, P],
+    "lnx_maxpool3s2": [P, P, I, I, I, I, I, P],
+    "lnx_dwconv3_fwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "lnx_se_scale": [P, P, P, I, I, I, I, P],
+    "lnx_attn_bias_fwd": [P, P, P, I, I, I, I, F, I, P],
     "lnx_rowscale": [P, P, P, L, I, I, I, P],
     "lnx_rope_table": [P, P, P, I, I, I, I, P],
     "lnx_rope_qk_fwd": [P, P, P, P, P, I, I, I, I, I, F, I, P],

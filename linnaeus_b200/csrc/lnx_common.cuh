@@ -198,6 +198,12 @@ __device__ __forceinline__ void gelu_both_tanh3_x2(float2 x, float2& gl, float2&
   dg = __ffma2_rn(hn, sm1, __ffma2_rn(t, f2(0.5f), f2(0.5f)));
 }
 
+// swish / SiLU = x sigmoid(x) = h (1 + tanh h), h = x / 2: one MUFU.TANH (bf16 tensor-core epilogues)
+__device__ __forceinline__ float swish_fast(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace lnx

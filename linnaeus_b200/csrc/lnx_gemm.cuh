@@ -35,6 +35,7 @@ __device__ __forceinline__ float gemm_epilogue_scalar(float v, int m, int n, lon
   } else {
     if (g.act == LNX_ACT_GELU || g.act == LNX_ACT_GELU_DG) v = gelu_f(v);
     else if (g.act == LNX_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (g.act == LNX_ACT_SWISH) v = v / (1.f + expf(-v));
   }
   if (g.col_scale) v *= g.col_scale[n];
   if (g.row_scale) v *= g.row_scale[m / g.rows_per_group];

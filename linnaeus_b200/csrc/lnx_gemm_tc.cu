@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         } else if (g.act == LNX_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+        } else if (g.act == LNX_ACT_SWISH) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vv[i] = swish_fast(vv[i]);
         }
         if (g.col_scale) {
           const float4 s0 = *reinterpret_cast<const float4*>(g.col_scale + n), s1 = *reinterpret_cast<const float4*>(g.col_scale + n + 4);

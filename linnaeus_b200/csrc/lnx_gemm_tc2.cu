@@ -431,6 +431,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
               } else if (ACT == LNX_ACT_RELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) vv[i] = fmaxf(vv[i], 0.f);
+              } else if (ACT == LNX_ACT_SWISH) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vv[i] = swish_fast(vv[i]);
               }
               if (SCALE) {
                 if (g.col_scale && n < p.N) {
@@ -661,6 +664,9 @@ int lnx_gemm_tc2(const GemmArgs& g, float* colsum_out, cudaStream_t st) {
     case LNX_ACT_NONE: return launch_none(L, in_kind, aux, scale, colsum);
     case LNX_ACT_GELU: return launch_act<LNX_ACT_GELU>(L, in_kind, aux, scale, colsum);
     case LNX_ACT_RELU: return launch_act<LNX_ACT_RELU>(L, in_kind, aux, scale, colsum);
+    case LNX_ACT_SWISH:
+      if (aux || in_kind || scale || colsum) return LNX_ERR_UNSUPPORTED;
+      return launch_variant<LNX_ACT_SWISH, 0, false, false, false>(L);
     case LNX_ACT_GELU_DG:
       if (!aux || in_kind || scale || colsum) return LNX_ERR_UNSUPPORTED;
       return launch_variant<LNX_ACT_GELU_DG, 0, true, false, false>(L);

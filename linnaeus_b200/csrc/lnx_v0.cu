@@ -1,0 +1,353 @@
+// mFormerV0 (RelativeAttention variant) inference kernels that the V1 path does not
+// already provide.  NHWC activations throughout.
+//   lnx_im2col3x3        dense 3x3 convs (stem, overlap patch embed) as gather + tensor-core GEMM
+//   lnx_maxpool3s2       MaxPool2d(3, 2, 1)
+//   lnx_dwconv3_fwd      depthwise 3x3 (stride 1 / 2, TF "same" static padding) + folded BN + swish, with the
+//                        squeeze-excite global average pool accumulated in the same pass
+//   lnx_se_scale         x * sigmoid(gate[b, c])
+//   lnx_attn_bias_fwd    softmax(scale q k^T + bias[h]) v for any head_dim <= 128, reading q/k/v straight out of the
+//                        [B, N, 3, heads, hd] qkv GEMM output (no split / transpose pass)
+// All HBM bound except the attention, which is a CUDA-core kernel in this round (head_dim 48 / 96).
+#include "lnx_common.cuh"
+
+using namespace lnx;
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ void zero16(Vec16<T>& v) {
+#pragma unroll
+  for (int i = 0; i < Vec16<T>::N; ++i) v.set(i, 0.f);
+}
+
+// ---------------------------------------------------------------- im2col 3x3 (pad 1), NHWC, C % V == 0
+template <typename T>
+__global__ void im2col3_nhwc_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int stride, int Ho, int Wo,
+                                    int Kpad) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const long long total = (long long)B * Ho * Wo * 9 * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int tap = (int)(r % 9);
+    r /= 9;  // output pixel index
+    const int wo = (int)(r % Wo);
+    const int ho = (int)((r / Wo) % Ho);
+    const long long b = r / ((long long)Wo * Ho);
+    const int h = ho * stride - 1 + tap / 3, w = wo * stride - 1 + tap % 3;
+    Vec16<T> v;
+    if (h >= 0 && h < H && w >= 0 && w < W) v = ld16(x + ((b * H + h) * W + w) * C + c * V);
+    else zero16(v);
+    st16(out + r * Kpad + tap * C + c * V, v);
+  }
+}
+
+// odd shapes (C not a multiple of the vector width, or zero-padded K): one thread per output element
+template <typename T>
+__global__ void im2col3_nhwc_scalar_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int stride, int Ho, int Wo,
+                                           int Kpad) {
+  const long long total = (long long)B * Ho * Wo * Kpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % Kpad);
+    const long long r = i / Kpad;
+    T v = from_f32<T>(0.f);
+    if (col < 9 * C) {
+      const int tap = col / C, c = col % C;
+      const int wo = (int)(r % Wo);
+      const int ho = (int)((r / Wo) % Ho);
+      const long long b = r / ((long long)Wo * Ho);
+      const int h = ho * stride - 1 + tap / 3, w = wo * stride - 1 + tap % 3;
+      if (h >= 0 && h < H && w >= 0 && w < W) v = x[((b * H + h) * W + w) * C + c];
+    }
+    out[i] = v;
+  }
+}
+
+// first conv: fp32 NCHW image, tiny Cin; one thread per output row, columns (kh, kw, c), zero padded to Kpad
+template <typename T>
+__global__ void im2col3_nchw_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int stride, int Ho, int Wo,
+                                    int Kpad) {
+  const long long total = (long long)B * Ho * Wo;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(r % Wo);
+    const int ho = (int)((r / Wo) % Ho);
+    const long long b = r / ((long long)Wo * Ho);
+    T* dst = out + r * Kpad;
+    int col = 0;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int h = ho * stride - 1 + tap / 3, w = wo * stride - 1 + tap % 3;
+      const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+      for (int c = 0; c < C; ++c, ++col) dst[col] = from_f32<T>(ok ? x[((b * C + c) * H + h) * W + w] : 0.f);
+    }
+    for (; col < Kpad; ++col) dst[col] = from_f32<T>(0.f);
+  }
+}
+
+// ---------------------------------------------------------------- maxpool 3x3 s2 p1
+template <typename T>
+__global__ void maxpool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int wo = (int)(r % Wo);
+    const int ho = (int)((r / Wo) % Ho);
+    const long long b = r / ((long long)Wo * Ho);
+    float m[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) m[e] = -INFINITY;
+    for (int dh = 0; dh < 3; ++dh) {
+      const int h = ho * 2 - 1 + dh;
+      if (h < 0 || h >= H) continue;
+      for (int dw = 0; dw < 3; ++dw) {
+        const int w = wo * 2 - 1 + dw;
+        if (w < 0 || w >= W) continue;
+        const Vec16<T> v = ld16(x + ((b * H + h) * W + w) * C + c * V);
+#pragma unroll
+        for (int e = 0; e < V; ++e) m[e] = fmaxf(m[e], v.get(e));
+      }
+    }
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < V; ++e) o.set(e, m[e]);
+    st16(y + r * C + c * V, o);
+  }
+}
+
+// ---------------------------------------------------------------- depthwise 3x3 + affine + swish (+ SE pool sums)
+// grid (pixel chunks, B); block (C / V, rows): every thread owns one channel vector and strides over the chunk's pixels
+template <typename T>
+__global__ void dwconv3_kernel(const T* __restrict__ x, const float* __restrict__ w9c, const float* __restrict__ scale,
+                               const float* __restrict__ shift, T* __restrict__ y, float* __restrict__ pool_sum, int H, int W, int C, int stride,
+                               int pad_t, int pad_l, int Ho, int Wo, int act, int pix_per_block) {
+  constexpr int V = Vec16<T>::N;
+  const int c0 = threadIdx.x * V;
+  const long long b = blockIdx.y;
+  float wr[9][V], sc[V], sh[V], psum[V];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int e = 0; e < V; ++e) wr[t][e] = w9c[t * C + c0 + e];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    sc[e] = scale ? scale[c0 + e] : 1.f;
+    sh[e] = shift ? shift[c0 + e] : 0.f;
+    psum[e] = 0.f;
+  }
+  const int p_begin = blockIdx.x * pix_per_block, p_end = min(Ho * Wo, p_begin + pix_per_block);
+  for (int p = p_begin + threadIdx.y; p < p_end; p += blockDim.y) {
+    const int ho = p / Wo, wo = p % Wo;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int h = ho * stride - pad_t + t / 3, w = wo * stride - pad_l + t % 3;
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        const Vec16<T> v = ld16(x + ((b * H + h) * W + w) * C + c0);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = fmaf(v.get(e), wr[t][e], acc[e]);
+      }
+    }
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float v = fmaf(acc[e], sc[e], sh[e]);
+      if (act == 1) v = v / (1.f + expf(-v));
+      o.set(e, v);
+      psum[e] += o.get(e);  // pool what the next layer will read (the rounded value)
+    }
+    st16(y + ((b * Ho + ho) * (long long)Wo + wo) * C + c0, o);
+  }
+  if (pool_sum) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) atomicAdd(pool_sum + b * C + c0 + e, psum[e]);
+  }
+}
+
+// ---------------------------------------------------------------- x * sigmoid(gate[b, c])
+template <typename T>
+__global__ void se_scale_kernel(const T* __restrict__ x, const float* __restrict__ gate, T* __restrict__ y, long long B, int HW, int C) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const long long total = B * HW * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    const long long b = i / ((long long)cv * HW);
+    Vec16<T> v = ld16(x + i * V);
+#pragma unroll
+    for (int e = 0; e < V; ++e) v.set(e, v.get(e) / (1.f + expf(-gate[b * C + c * V + e])));
+    st16(y + i * V, v);
+  }
+}
+
+// ---------------------------------------------------------------- attention with additive bias, generic head dim
+constexpr int AKT = 32;  // keys per shared tile
+template <typename T, int HDIM>
+__global__ void __launch_bounds__(64) attn_bias_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ bias, T* __restrict__ out,
+                                                           int heads, int N, float scale) {
+  __shared__ __align__(16) float Ks[AKT * HDIM];
+  __shared__ __align__(16) float Vs[AKT * HDIM];
+  const int bh = blockIdx.y;
+  const int b = bh / heads, h = bh % heads;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < N;
+  const long long row_stride = 3LL * heads * HDIM;  // elements per token in qkv
+  const T* base = qkv + (long long)b * N * row_stride + (long long)h * HDIM;
+  float qr[HDIM], o[HDIM];
+#pragma unroll
+  for (int d = 0; d < HDIM; ++d) {
+    qr[d] = valid ? to_f32(base[(long long)i * row_stride + d]) * scale : 0.f;
+    o[d] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  const float* brow = bias ? bias + ((long long)h * N + (valid ? i : 0)) * N : nullptr;
+  for (int j0 = 0; j0 < N; j0 += AKT) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < AKT * HDIM; t += blockDim.x) {
+      const int r = t / HDIM, d = t % HDIM;
+      float kv = 0.f, vv = 0.f;
+      if (j0 + r < N) {
+        const T* tok = base + (long long)(j0 + r) * row_stride;
+        kv = to_f32(tok[(long long)heads * HDIM + d]);
+        vv = to_f32(tok[2LL * heads * HDIM + d]);
+      }
+      Ks[t] = kv;
+      Vs[t] = vv;
+    }
+    __syncthreads();
+    const int jn = min(AKT, N - j0);
+    for (int jc = 0; jc < jn; ++jc) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < HDIM; ++d) a = fmaf(qr[d], Ks[jc * HDIM + d], a);
+      if (brow) a += brow[j0 + jc];
+      const float mn = fmaxf(m, a);
+      const float corr = __expf(m - mn);
+      const float pe = __expf(a - mn);
+      l = l * corr + pe;
+#pragma unroll
+      for (int d = 0; d < HDIM; ++d) o[d] = fmaf(o[d], corr, pe * Vs[jc * HDIM + d]);
+      m = mn;
+    }
+  }
+  if (valid) {
+    const float inv = 1.f / l;
+    T* dst = out + ((long long)b * N + i) * heads * HDIM + (long long)h * HDIM;
+#pragma unroll
+    for (int d = 0; d < HDIM; ++d) dst[d] = from_f32<T>(o[d] * inv);
+  }
+}
+
+inline int grid_for(long long total, int threads) { return (int)max(1LL, min((long long)kNumSMs * 16, (total + threads - 1) / threads)); }
+
+}  // namespace
+
+extern "C" int lnx_im2col3x3(const void* x, int x_is_nchw_f32, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo, int Kpad,
+                             int dtype, lnx_stream_t s) {
+  LNX_REQUIRE(x && out, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && (stride == 1 || stride == 2) && Kpad >= 9 * C, LNX_ERR_SHAPE);
+  LNX_REQUIRE(Ho == (H + 2 - 3) / stride + 1 && Wo == (W + 2 - 3) / stride + 1, LNX_ERR_SHAPE);
+  cudaStream_t st = (cudaStream_t)s;
+  if (x_is_nchw_f32) {
+    const long long total = (long long)B * Ho * Wo;
+    if (dtype == LNX_F32) im2col3_nchw_kernel<float><<<grid_for(total, 128), 128, 0, st>>>((const float*)x, (float*)out, B, H, W, C, stride, Ho, Wo, Kpad);
+    else if (dtype == LNX_BF16) im2col3_nchw_kernel<bf16><<<grid_for(total, 128), 128, 0, st>>>((const float*)x, (bf16*)out, B, H, W, C, stride, Ho, Wo, Kpad);
+    else return LNX_ERR_DTYPE;
+  } else {
+    const int V = dtype == LNX_F32 ? 4 : 8;
+    LNX_REQUIRE(dtype == LNX_F32 || dtype == LNX_BF16, LNX_ERR_DTYPE);
+    if (C % V != 0 || Kpad != 9 * C) {
+      const long long total = (long long)B * Ho * Wo * Kpad;
+      if (dtype == LNX_F32) im2col3_nhwc_scalar_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)out, B, H, W, C, stride, Ho, Wo, Kpad);
+      else im2col3_nhwc_scalar_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)out, B, H, W, C, stride, Ho, Wo, Kpad);
+    } else {
+      LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(out), LNX_ERR_ALIGN);
+      const long long total = (long long)B * Ho * Wo * 9 * (C / V);
+      if (dtype == LNX_F32) im2col3_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (float*)out, B, H, W, C, stride, Ho, Wo, Kpad);
+      else im2col3_nhwc_kernel<bf16><<<grid_for(total, 256), 256, 0, st>>>((const bf16*)x, (bf16*)out, B, H, W, C, stride, Ho, Wo, Kpad);
+    }
+  }
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+extern "C" int lnx_maxpool3s2(const void* x, void* y, int B, int H, int W, int C, int dtype, lnx_stream_t s) {
+  LNX_REQUIRE(x && y, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, LNX_ERR_SHAPE);
+  LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(y), LNX_ERR_ALIGN);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  cudaStream_t st = (cudaStream_t)s;
+  if (dtype == LNX_F32) {
+    LNX_REQUIRE(C % 4 == 0, LNX_ERR_SHAPE);
+    maxpool3s2_kernel<float><<<grid_for((long long)B * Ho * Wo * (C / 4), 256), 256, 0, st>>>((const float*)x, (float*)y, B, H, W, C, Ho, Wo);
+  } else if (dtype == LNX_BF16) {
+    LNX_REQUIRE(C % 8 == 0, LNX_ERR_SHAPE);
+    maxpool3s2_kernel<bf16><<<grid_for((long long)B * Ho * Wo * (C / 8), 256), 256, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, Ho, Wo);
+  } else
+    return LNX_ERR_DTYPE;
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+extern "C" int lnx_dwconv3_fwd(const void* x, const float* w9c, const float* scale, const float* shift, void* y, float* pool_sum, int B, int H,
+                               int W, int C, int stride, int pad_t, int pad_l, int Ho, int Wo, int act, int dtype, lnx_stream_t s) {
+  LNX_REQUIRE(x && w9c && y, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && (stride == 1 || stride == 2), LNX_ERR_SHAPE);
+  LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(y), LNX_ERR_ALIGN);
+  const int V = dtype == LNX_F32 ? 4 : 8;
+  LNX_REQUIRE(dtype == LNX_F32 || dtype == LNX_BF16, LNX_ERR_DTYPE);
+  LNX_REQUIRE(C % V == 0 && C / V <= 1024, LNX_ERR_SHAPE);
+  const int tx = C / V;
+  const int ty = max(1, 256 / tx);
+  const int ppb = 64;
+  dim3 grid((Ho * Wo + ppb - 1) / ppb, B), block(tx, ty);
+  cudaStream_t st = (cudaStream_t)s;
+  if (dtype == LNX_F32)
+    dwconv3_kernel<float><<<grid, block, 0, st>>>((const float*)x, w9c, scale, shift, (float*)y, pool_sum, H, W, C, stride, pad_t, pad_l, Ho, Wo, act, ppb);
+  else
+    dwconv3_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, w9c, scale, shift, (bf16*)y, pool_sum, H, W, C, stride, pad_t, pad_l, Ho, Wo, act, ppb);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+extern "C" int lnx_se_scale(const void* x, const float* gate, void* y, int B, int HW, int C, int dtype, lnx_stream_t s) {
+  LNX_REQUIRE(x && gate && y, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && HW > 0 && C > 0, LNX_ERR_SHAPE);
+  LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(y), LNX_ERR_ALIGN);
+  cudaStream_t st = (cudaStream_t)s;
+  if (dtype == LNX_F32) {
+    LNX_REQUIRE(C % 4 == 0, LNX_ERR_SHAPE);
+    se_scale_kernel<float><<<grid_for((long long)B * HW * (C / 4), 256), 256, 0, st>>>((const float*)x, gate, (float*)y, B, HW, C);
+  } else if (dtype == LNX_BF16) {
+    LNX_REQUIRE(C % 8 == 0, LNX_ERR_SHAPE);
+    se_scale_kernel<bf16><<<grid_for((long long)B * HW * (C / 8), 256), 256, 0, st>>>((const bf16*)x, gate, (bf16*)y, B, HW, C);
+  } else
+    return LNX_ERR_DTYPE;
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+extern "C" int lnx_attn_bias_fwd(const void* qkv, const float* bias, void* out, int B, int heads, int N, int hd, float scale, int dtype,
+                                 lnx_stream_t s) {
+  LNX_REQUIRE(qkv && out, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && heads > 0 && N > 0, LNX_ERR_SHAPE);
+  LNX_REQUIRE(dtype == LNX_F32 || dtype == LNX_BF16, LNX_ERR_DTYPE);
+  dim3 grid((N + 63) / 64, B * heads);
+  cudaStream_t st = (cudaStream_t)s;
+#define LNX_AB(HDIM)                                                                                                                   \
+  case HDIM:                                                                                                                           \
+    if (dtype == LNX_F32) attn_bias_fwd_kernel<float, HDIM><<<grid, 64, 0, st>>>((const float*)qkv, bias, (float*)out, heads, N, scale); \
+    else attn_bias_fwd_kernel<bf16, HDIM><<<grid, 64, 0, st>>>((const bf16*)qkv, bias, (bf16*)out, heads, N, scale);                     \
+    break;
+  switch (hd) {
+    LNX_AB(16) LNX_AB(32) LNX_AB(48) LNX_AB(64) LNX_AB(96) LNX_AB(128)
+    default: return LNX_ERR_UNSUPPORTED;
+  }
+#undef LNX_AB
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}

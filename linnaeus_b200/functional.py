@@ -17,7 +17,7 @@ from ._lib import ACT_GELU, ACT_GELU_DG, ACT_MUL, ACT_NONE, ACT_RELU, call, dt, 
 # set by tests to force the CUDA-core kernels instead of tcgen05 ones
 FORCE_SIMT = False
 
-_ACT = {None: ACT_NONE, "none": ACT_NONE, "gelu": ACT_GELU, "relu": ACT_RELU}
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "gelu": ACT_GELU, "relu": ACT_RELU, "swish": _lib.ACT_SWISH}
 
 
 def _c(t: torch.Tensor) -> torch.Tensor:

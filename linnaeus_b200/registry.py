@@ -77,7 +77,7 @@ def install_into_linnaeus() -> list[str]:
     (``linnaeus.models.model_factory``); returns the names replaced."""
     from linnaeus.models import model_factory as mf  # the reference package must be importable
 
-    from . import mformer_v1  # noqa: F401  (populates _model_registry)
+    from . import mformer_v0, mformer_v1  # noqa: F401  (populate _model_registry)
 
     names = []
     for name, cls in _model_registry.items():
