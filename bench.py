@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FWD_GFLOP = {"sm": 8.659, "md": 12.505, "xl": 448.16}  # per image (SURVEY.md section 6, 224^2; xl at 384^2)
+FWD_GFLOP_V0 = {"sm": 8.94}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (profiles/r01_kernels_summary.md),
 # keyed by (variant, per-GPU batch, image size, dtype); None when that exact shape was not captured
 NCU_TRAFFIC_BYTES = {}
@@ -38,6 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="sm")
+    ap.add_argument("--arch", default="v1", choices=["v1", "v0"], help="mFormerV1 (train / infer) or mFormerV0 (RelativeAttention variant, infer only)")
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--img", type=int, default=224)
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
@@ -119,15 +121,24 @@ def cpu_train_baseline(variant: str, img: int, batch: int, steps: int = 3, warmu
     return batch / med, med, torch.get_num_threads()
 
 
-def cpu_infer_baseline(variant: str, img: int, batch: int, steps: int = 5, warmup: int = 2):
-    from linnaeus_b200.config import make_synthetic_config
-    from oracle import mformer_oracle as O
+def cpu_infer_baseline(variant: str, img: int, batch: int, steps: int = 5, warmup: int = 2, arch: str = "v1"):
+    from linnaeus_b200.config import make_synthetic_config, make_synthetic_config_v0
 
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg, nc = make_synthetic_config(variant, img)
-    a = O.arch_from_config(cfg, nc)
-    P = O.synth_state_dict(O.param_shapes(a), 0)
-    x, meta, _ = O.synth_batch(a, batch, 0)
+    if arch == "v0":
+        from oracle import mformer_v0_oracle as O
+
+        cfg, nc = make_synthetic_config_v0(variant, img)
+        a = O.arch_from_config(cfg, nc)
+        P = O.synth_state_dict(a, 0)
+        x, meta = O.synth_batch(a, batch, 0)
+    else:
+        from oracle import mformer_oracle as O
+
+        cfg, nc = make_synthetic_config(variant, img)
+        a = O.arch_from_config(cfg, nc)
+        P = O.synth_state_dict(O.param_shapes(a), 0)
+        x, meta, _ = O.synth_batch(a, batch, 0)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -149,12 +160,17 @@ def run_reference(args):
     fn = cpu_train_baseline if args.mode == "train" else cpu_infer_baseline
     b = args.cpu_batch
     t0 = time.perf_counter()
-    val, med, cores = fn(args.variant, args.img, b, steps=args.steps, warmup=args.warmup)
+    if args.arch == "v0":
+        if args.mode != "infer":
+            raise SystemExit("--arch v0 is the inference benchmark (config 5): use --mode infer")
+        val, med, cores = cpu_infer_baseline(args.variant, args.img, b, steps=args.steps, warmup=args.warmup, arch="v0")
+    else:
+        val, med, cores = fn(args.variant, args.img, b, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference",
         "metric": metric, "value": val, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"mFormerV1_{args.variant} {args.mode} step {args.img}x{args.img}, 6 ranks, 3 meta comps (host CPU, oracle port)",
+        "config": {"workload": f"mFormer{args.arch.upper()}_{args.variant} {args.mode} step {args.img}x{args.img}, 6 ranks, 3 meta comps (host CPU, oracle port)",
                    "per_gpu_batch": args.batch, "cpu_sample_batch": b},
         "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of batch {b} (median), {args.warmup} warm-up; oracle/mformer_oracle.py (fp32, torch CPU ops)"},
@@ -187,7 +203,12 @@ def run_b200(args):
     _lib.load()
 
     B, S = args.batch, args.img
-    cfg, nc = L.make_synthetic_config(args.variant, S)
+    if args.arch == "v0":
+        if args.mode != "infer":
+            raise SystemExit("--arch v0 is the inference benchmark (config 5): use --mode infer")
+        cfg, nc = L.make_synthetic_config_v0(args.variant, S)
+    else:
+        cfg, nc = L.make_synthetic_config(args.variant, S)
     torch.manual_seed(0)
     model = L.build_model(cfg, nc).to(dev)
     cd = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -206,6 +227,9 @@ def run_b200(args):
     sampler = ClockSampler(local)
     hbm, tf_burst, tf_sus, peak_src = peaks()
 
+    # small-batch inference keeps its whole working set inside the 126 MB L2: flush it between timed iterations then
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if (args.mode == "infer" and B * S * S < 64 * 224 * 224) else None
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -213,17 +237,30 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
+        if l2_flush is None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total = e0.elapsed_time(e1)
+        else:  # per-step events around fn only; the flush (a 256 MB fill) runs between them
+            evs = []
+            for _ in range(steps):
+                l2_flush.zero_()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                fn()
+                a1.record()
+                evs.append((a0, a1))
+            torch.cuda.synchronize()
+            total = sum(a0.elapsed_time(a1) for a0, a1 in evs)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([total], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, (_lib.launch_count - l0)
@@ -250,14 +287,35 @@ def run_b200(args):
         flop_mult = 3.0
     else:
         model.eval()
+        use_graph = not args.no_graph
+        s_img, s_meta = d_img.clone(), d_meta.clone()
         def fwd(img, meta):
             with torch.no_grad():
                 return model(img, meta)
-        resident = lambda: fwd(d_img, d_meta)  # noqa: E731
-        def e2e_step():
-            out = fwd(h_img.to(dev, non_blocking=True), h_meta.to(dev, non_blocking=True))
-            return out.cat[:, :8].float().cpu()
-        use_graph = False
+        if use_graph:  # one CUDA graph per forward over static input buffers (same mechanism as TrainStep.capture)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fwd(s_img, s_meta)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count
+            with torch.cuda.graph(graph):
+                s_out = fwd(s_img, s_meta)
+            infer_launches = _lib.launch_count - n0
+            resident = lambda: graph.replay()  # noqa: E731
+            def e2e_step():
+                s_img.copy_(h_img, non_blocking=True)
+                s_meta.copy_(h_meta, non_blocking=True)
+                graph.replay()
+                return s_out.cat[:, :8].float().cpu()
+        else:
+            resident = lambda: fwd(d_img, d_meta)  # noqa: E731
+            def e2e_step():
+                out = fwd(h_img.to(dev, non_blocking=True), h_meta.to(dev, non_blocking=True))
+                return out.cat[:, :8].float().cpu()
         metric = "infer_img_per_s"
         flop_mult = 1.0
 
@@ -267,39 +325,51 @@ def run_b200(args):
     ms_e2e, _ = timed(e2e_step, max(3, args.steps // 2), 2)
     value = B * world / (ms / 1e3)
     e2e = B * world / (ms_e2e / 1e3)
-    if use_graph:
+    if use_graph and args.mode == "train":
         launches = ts.launches_per_step * args.steps if hasattr(ts, "launches_per_step") else launches
+    elif use_graph:
+        launches = infer_launches * args.steps
 
     # roofline of the dominant kernel, timed live: the stage-0 pointwise-expand GEMM of the ConvNeXt blocks exactly as the
     # training step launches it (gemm_tc2_kernel<GELU_DG, aux>: bias + GELU, gelu'(pre) saved as second output).  K = 96:
     # HBM bound, algorithmic bytes = A + W + 2 outputs.  `traffic` = dram bytes per launch of this kernel from the ncu
     # --set full capture committed under profiles/ (B = 256 shape only).
     import linnaeus_b200.functional as F
-    M, K, N = B * (S // 4) ** 2, cfg.MODEL.CONVNEXT_STAGES.DIMS[0], 4 * cfg.MODEL.CONVNEXT_STAGES.DIMS[0]
+    if args.arch == "v0":  # stage_1 expand 1x1 conv (+folded BN, swish): one output
+        M, K, N = B * (S // 4) ** 2, cfg.MODEL.CONV_STAGES.EMBED_DIMS[0], 4 * cfg.MODEL.CONV_STAGES.EMBED_DIMS[0]
+        act_code, n_out, kname = 5, 1, "gemm_tc2_kernel<SWISH> (MBConv expand stage 1: M=%d K=%d N=%d, folded BN + swish)"
+    else:
+        M, K, N = B * (S // 4) ** 2, cfg.MODEL.CONVNEXT_STAGES.DIMS[0], 4 * cfg.MODEL.CONVNEXT_STAGES.DIMS[0]
+        act_code, n_out, kname = 3, 2, "gemm_tc2_kernel<GELU_DG, aux> (pwconv1 stage 0: M=%d K=%d N=%d, bias+GELU, saves gelu')"
     esz = 2 if cd == torch.bfloat16 else 4
     a_ = torch.randn(M, K, device=dev).to(cd)
     w_ = torch.randn(N, K, device=dev).to(cd)
     b_ = torch.randn(N, device=dev)
-    o_, aux_ = torch.empty(M, N, device=dev, dtype=cd), torch.empty(M, N, device=dev, dtype=cd)
+    o_ = torch.empty(M, N, device=dev, dtype=cd)
+    aux_ = torch.empty(M, N, device=dev, dtype=cd) if n_out == 2 else None
     def gemm():
-        F.gemm(a_, w_, M, N, K, out=o_, bias=b_, act=3, aux_out=aux_)
+        F.gemm(a_, w_, M, N, K, out=o_, bias=b_, act=act_code, aux_out=aux_)
     kms, _ = timed(gemm, 20, 3)
-    alg_bytes = (M * K + N * K + 2 * M * N) * esz
+    alg_bytes = (M * K + N * K + n_out * M * N) * esz
     ach = alg_bytes / (kms / 1e3) / 1e9
     traffic = NCU_TRAFFIC_BYTES.get((args.variant, B, S, args.dtype))
-    roofline = {"bound": "hbm", "kernel": "gemm_tc2_kernel<GELU_DG, aux> (pwconv1 stage 0: M=%d K=%d N=%d, bias+GELU, saves gelu')" % (M, K, N),
+    gflop = (FWD_GFLOP_V0 if args.arch == "v0" else FWD_GFLOP).get(args.variant, 0.0)
+    roofline = {"bound": "hbm", "kernel": kname % (M, K, N),
                 "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes": alg_bytes, "ms_per_launch": kms,
-                "model_tflops": value * FWD_GFLOP.get(args.variant, 0.0) * flop_mult / 1e3,
-                "model_frac_of_bf16_sustained": value * FWD_GFLOP.get(args.variant, 0.0) * flop_mult / 1e3 / tf_sus}
+                "model_tflops": value * gflop * flop_mult / 1e3,
+                "model_frac_of_bf16_sustained": value * gflop * flop_mult / 1e3 / tf_sus}
 
     line = {
         "metric": metric, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"mFormerV1_{args.variant} {args.mode} step (fwd+6-rank CE loss+bwd+clip+AdamW) {S}x{S}, 3 meta comps, random init",
+        "config": {"workload": (f"mFormerV1_{args.variant} train step (fwd+6-rank CE loss+bwd+clip+AdamW) {S}x{S}, 3 meta comps, random init"
+                                if args.mode == "train" else
+                                f"mFormer{args.arch.upper()}_{args.variant} inference (eval forward, 6 rank heads) {S}x{S}, 3 meta comps, random init"),
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
-                   "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                   "l2_policy": ("inputs+activations per step exceed the 126 MB L2; no explicit flush" if l2_flush is None
+                                 else "256 MB fill between timed iterations (working set fits in L2); per-iteration CUDA events"),
                    "drop_path": 0.0},
         "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d if args.mode == "train" else h_img.numel() * 4 + h_meta.numel() * 4,
                 "d2h_bytes_per_step": 4 if args.mode == "train" else B * 8 * 4, "ms_per_step": ms_e2e},
@@ -308,10 +378,13 @@ def run_b200(args):
         "roofline": roofline,
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        fn = cpu_train_baseline if args.mode == "train" else cpu_infer_baseline
-        v, med, cores = fn(args.variant, S, args.cpu_batch, steps=3, warmup=1)
+        if args.mode == "train":
+            v, med, cores = cpu_train_baseline(args.variant, S, args.cpu_batch, steps=3, warmup=1)
+        else:
+            v, med, cores = cpu_infer_baseline(args.variant, S, args.cpu_batch, steps=3, warmup=1, arch=args.arch)
         line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
-                                "sample": f"3 steps of batch {args.cpu_batch} (median) of the same workload in fp32; oracle/mformer_oracle.py"}
+                                "sample": f"3 steps of batch {args.cpu_batch} (median) of the same workload in fp32; "
+                                          + ("oracle/mformer_v0_oracle.py" if args.arch == "v0" else "oracle/mformer_oracle.py")}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
