@@ -18,6 +18,9 @@
 // by 256 threads (two per query row) as bf16 into smem, then dV += P^T dO, dK += dS^T Q, dQ[query tile] += dS K.
 // TMEM holds S, dP, dV, dK and BOTH dQ tiles (512 columns exactly), so dQ never leaves the chip until it is final:
 // no fp32 atomics, no zero fill, no cast pass.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "lnx_tc_common.cuh"
 
 using namespace lnx;
@@ -53,6 +56,10 @@ struct FwdParams {
   int B, heads, N, nkp;  // nkp = keys rounded up to 16
   int n_qt, n_bh;
   int c_split;           // first key column of the second softmax half (multiple of 16)
+  int hd;                // head dim <= 64 (tiles are zero padded to 64 by the TMA out-of-bounds fill)
+  int qkv4d;             // 1: q/k/v are read straight from a [B, N, 3, heads, hd] qkv matrix (4-D tensor maps)
+  float scale;           // logits = scale * q k^T (+ bias); 1 when q arrives pre-scaled
+  const float* bias;     // nullable, [heads, N, N] added to the scaled logits (relative position bias)
 };
 
 // barrier indices
@@ -70,7 +77,8 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
   const int p_blocks = (p.nkp + 63) / 64;
   float* sMax = reinterpret_cast<float*>(sP + (size_t)p_blocks * 16384);  // [2 TMEM buffers][2 halves][128]
   float* sSum = sMax + 512;                                             // [2][2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 512);
+  float* sBias = sSum + 512;                                            // [8 softmax warps][32 rows][17] (bias staging, when p.bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + (p.bias ? 8 * 32 * 17 : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,13 +115,20 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
         const int kvs = j & 1;
         mbar_wait_relaxed(&bars[KV_EMPTY + kvs], (((uint32_t)j >> 1) & 1u) ^ 1u);
         mbar_expect_tx(&bars[KV_FULL + kvs], 2 * (uint32_t)kv_bytes);
-        tma_load_3d(sKV + (size_t)kvs * 2 * kv_bytes, &tmK, &bars[KV_FULL + kvs], 0, 0, bh);
-        tma_load_3d(sKV + (size_t)kvs * 2 * kv_bytes + kv_bytes, &tmV, &bars[KV_FULL + kvs], 0, 0, bh);
+        const int b_ = bh / p.heads, h_ = bh - b_ * p.heads;
+        if (p.qkv4d) {
+          tma_load_4d(sKV + (size_t)kvs * 2 * kv_bytes, &tmK, &bars[KV_FULL + kvs], 0, h_, 0, b_);
+          tma_load_4d(sKV + (size_t)kvs * 2 * kv_bytes + kv_bytes, &tmV, &bars[KV_FULL + kvs], 0, h_, 0, b_);
+        } else {
+          tma_load_3d(sKV + (size_t)kvs * 2 * kv_bytes, &tmK, &bars[KV_FULL + kvs], 0, 0, bh);
+          tma_load_3d(sKV + (size_t)kvs * 2 * kv_bytes + kv_bytes, &tmV, &bars[KV_FULL + kvs], 0, 0, bh);
+        }
         for (int qt = 0; qt < p.n_qt; ++qt, ++t) {
           const int qs = t & 1;
           mbar_wait_relaxed(&bars[Q_EMPTY + qs], (((uint32_t)t >> 1) & 1u) ^ 1u);
           mbar_expect_tx(&bars[Q_FULL + qs], 16384);
-          tma_load_3d(sQ + qs * 16384, &tmQ, &bars[Q_FULL + qs], 0, qt * QT, bh);
+          if (p.qkv4d) tma_load_4d(sQ + qs * 16384, &tmQ, &bars[Q_FULL + qs], 0, h_, qt * QT, b_);
+          else tma_load_3d(sQ + qs * 16384, &tmQ, &bars[Q_FULL + qs], 0, qt * QT, bh);
         }
       }
     }
@@ -167,34 +182,60 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
       float* bSum = sSum + buf * 256;
       mbar_wait(&bars[S_FULL + buf], ((uint32_t)t >> 1) & 1u);
       tcgen05_fence_after();
-      // pass 1: row max over this half's valid keys
+      // logits = scale * S (+ bias).  The bias chunk [32 rows x 16 keys] of this warp is staged through shared memory with
+      // coalesced 16-byte loads (a lane owns one ROW, so direct loads would touch 32 cache lines per instruction).
+      const int j_ = t / p.n_qt, qt_ = t - j_ * p.n_qt;
+      const int bh_ = (int)blockIdx.x + j_ * (int)gridDim.x;
+      const float sl = p.scale * LOG2E;
+      float* wb = sBias + sw * (32 * 17);
+      const float* bhead = p.bias ? p.bias + (long long)(bh_ % p.heads) * p.N * p.N : nullptr;
+      auto stage_bias = [&](int c) {
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 8 + (lane >> 2), c4 = c + (lane & 3) * 4;
+          const int gm = min(qt_ * QT + q * 32 + rl, p.N - 1);  // rows past N read row N - 1 (never stored)
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c4 < p.N) bv = __ldg(reinterpret_cast<const float4*>(bhead + (long long)gm * p.N + c4));  // N % 4 == 0
+          float* d = wb + rl * 17 + (lane & 3) * 4;
+          d[0] = bv.x; d[1] = bv.y; d[2] = bv.z; d[3] = bv.w;
+        }
+        __syncwarp();
+      };
+      // pass 1: row max over this half's valid keys (in the log2 domain)
       float mx = -INFINITY;
       for (int c = c_begin; c < c_end; c += 16) {
         float v[16];
         tmem_ld16(trow + c, v);
-        if (c + 16 <= p.N) {
+        if (bhead) stage_bias(c);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c + i < p.N) mx = fmaxf(mx, v[i]);
+        for (int i = 0; i < 16; ++i) {
+          if (c + i < p.N) {
+            float a = v[i] * sl;
+            if (bhead) a = fmaf(wb[lane * 17 + i], LOG2E, a);
+            mx = fmaxf(mx, a);
+          }
         }
       }
       bMax[half * 128 + r] = mx;
       named_bar(1, 256);
       mx = fmaxf(mx, bMax[(half ^ 1) * 128 + r]);
-      const float mxl = mx * LOG2E;
+      const float mxl = mx;
       mbar_wait(&bars[P_EMPTY], ((uint32_t)t & 1u) ^ 1u);  // P V of the previous item has consumed the P tile
-      // pass 2: P = exp(S - max) -> bf16 smem, row sum in fp32
+      // pass 2: P = exp2(logit - max) -> bf16 smem, row sum in fp32
       float sum = 0.f;
       for (int c = c_begin; c < c_end; c += 16) {
         float v[16];
         tmem_ld16(trow + c, v);
+        if (bhead) stage_bias(c);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float e = ex2f(fmaf(v[i], LOG2E, -mxl));
-          if (c + 16 > p.N && c + i >= p.N) e = 0.f;
+          float e = 0.f;
+          if (c + i < p.N) {
+            float a = fmaf(v[i], sl, -mxl);
+            if (bhead) a = fmaf(wb[lane * 17 + i], LOG2E, a);
+            e = ex2f(a);
+          }
           sum += e;
           v[i] = e;
         }
@@ -221,20 +262,19 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
       const float mx = fmaxf(sMax[buf * 256 + r], sMax[buf * 256 + 128 + r]);
       const float inv = 1.0f / sum;
       const int b = bh / p.heads, h = bh - b * p.heads;
-#pragma unroll
-      for (int c = 0; c < HD; c += 16) {
+      for (int c = 0; c < p.hd; c += 16) {
         float v[16];
         __syncwarp();
         tmem_ld16(trow + c, v);
         if (m < p.N) {
-          bf16* dst = out + (((long long)b * p.N + m) * p.heads + h) * HD + c;
+          bf16* dst = out + (((long long)b * p.N + m) * p.heads + h) * p.hd + c;
           *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(v[0] * inv, v[1] * inv), pack2(v[2] * inv, v[3] * inv), pack2(v[4] * inv, v[5] * inv),
                                                       pack2(v[6] * inv, v[7] * inv));
           *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pack2(v[8] * inv, v[9] * inv), pack2(v[10] * inv, v[11] * inv),
                                                           pack2(v[12] * inv, v[13] * inv), pack2(v[14] * inv, v[15] * inv));
         }
       }
-      if (m < p.N) lse[(long long)bh * p.N + m] = mx + __logf(sum);
+      if (lse && m < p.N) lse[(long long)bh * p.N + m] = mx * (1.0f / LOG2E) + __logf(sum);  // mx is kept in the log2 domain
       tcgen05_fence_before();
       mbar_arrive(&bars[T_EMPTY + buf]);
     }
@@ -680,6 +720,8 @@ bool head_tmap(CUtensorMap* tm, const void* ptr, int BH, int N, int box_rows) {
   return make_tmap(tm, ptr, 3, dims, strides, box);
 }
 
+int g_fwd_smem_set = 0;  // largest dynamic shared-memory size attn_fwd_tc2_kernel has been configured for
+
 }  // namespace
 
 int lnx_attn_fwd_tc2(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd, cudaStream_t st) {
@@ -690,17 +732,53 @@ int lnx_attn_fwd_tc2(const void* q, const void* k, const void* v, void* out, flo
   p.n_qt = (N + QT - 1) / QT;
   p.n_bh = B * heads;
   p.c_split = ((p.nkp / 16 + 1) / 2) * 16;
+  p.hd = HD; p.qkv4d = 0; p.scale = 1.0f; p.bias = nullptr;
   CUtensorMap tq, tk, tv;
   if (!head_tmap(&tq, q, p.n_bh, N, QT) || !head_tmap(&tk, k, p.n_bh, N, p.nkp) || !head_tmap(&tv, v, p.n_bh, N, p.nkp)) return LNX_ERR_UNSUPPORTED;
   const size_t smem = 1024 + 4 * (size_t)p.nkp * 128 + 2 * 16384 + (size_t)((p.nkp + 63) / 64) * 16384 + 8 * 128 * 4 + NBARS * 8 + 64;
   if (smem > 232448) return LNX_ERR_UNSUPPORTED;
-  static int smem_set = 0;
-  if ((int)smem > smem_set) {
+  if ((int)smem > g_fwd_smem_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return lnx_set_cuda_error(e);
-    smem_set = (int)smem;
+    g_fwd_smem_set = (int)smem;
   }
   attn_fwd_tc2_kernel<<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tq, tk, tv, (bf16*)out, lse, p);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+// softmax(scale q k^T + bias[h]) v with q/k/v read straight from qkv [B, N, 3, heads, hd] (hd <= 64, N <= 240): the
+// RelativeAttention of mFormerV0.  Head dims below 64 ride on the TMA out-of-bounds zero fill (tiles stay [rows][64]).
+int lnx_attn_bias_fwd_tc2(const void* qkv, const float* bias, void* out, int B, int heads, int N, int hd, float scale, cudaStream_t st) {
+  if (hd > HD || hd % 16 != 0 || N > 240 || N < 1) return LNX_ERR_UNSUPPORTED;
+  if (!lnx_aligned16(qkv) || !lnx_aligned16(out)) return LNX_ERR_UNSUPPORTED;
+  if (bias && (N % 4 != 0 || !lnx_aligned16(bias))) return LNX_ERR_UNSUPPORTED;  // the bias rows are staged with 16-byte loads
+  FwdParams p;
+  p.B = B; p.heads = heads; p.N = N;
+  p.nkp = (N + 15) / 16 * 16;
+  p.n_qt = (N + QT - 1) / QT;
+  p.n_bh = B * heads;
+  p.c_split = ((p.nkp / 16 + 1) / 2) * 16;
+  p.hd = hd; p.qkv4d = 1; p.scale = scale; p.bias = bias;
+  CUtensorMap tm[3];
+  for (int which = 0; which < 3; ++which) {
+    const long long dims[4] = {hd, heads, N, B};
+    const long long strides[3] = {hd, 3LL * heads * hd, (long long)N * 3 * heads * hd};
+    const int box[4] = {HD, 1, which == 0 ? QT : p.nkp, 1};
+    if (!make_tmap(&tm[which], reinterpret_cast<const bf16*>(qkv) + (long long)which * heads * hd, 4, dims, strides, box)) {
+      if (getenv("LNX_ATTN_NO_FALLBACK")) fprintf(stderr, "lnx_attn_bias_fwd_tc2: tensor map %d failed (hd %d heads %d N %d B %d)\n", which, hd, heads, N, B);
+      return LNX_ERR_UNSUPPORTED;
+    }
+  }
+  const size_t smem = 1024 + 4 * (size_t)p.nkp * 128 + 2 * 16384 + (size_t)((p.nkp + 63) / 64) * 16384 + 8 * 128 * 4 + (bias ? 8 * 32 * 17 * 4 : 0) +
+                      NBARS * 8 + 64;
+  if (smem > 232448) return LNX_ERR_UNSUPPORTED;
+  if (smem > (size_t)g_fwd_smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return lnx_set_cuda_error(e);
+    g_fwd_smem_set = (int)smem;
+  }
+  attn_fwd_tc2_kernel<<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tm[0], tm[1], tm[2], (bf16*)out, nullptr, p);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }

@@ -69,6 +69,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -155,14 +162,14 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor map, 128B swizzle, zero OOB fill. rank 2: [outer][inner]; rank 3: [d2][d1][inner].
+// bf16 tensor map, 128B swizzle, zero OOB fill. rank 2: [outer][inner]; rank 3: [d2][d1][inner]; rank 4 likewise.
 inline bool make_tmap(CUtensorMap* tm, const void* ptr, int rank, const long long* dims, const long long* strides_elems,
                       const int* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto enc = get_encode_fn();
   if (!enc) return false;
-  cuuint64_t d[3];
-  cuuint64_t s[2];
-  cuuint32_t b[3], e[3] = {1u, 1u, 1u};
+  cuuint64_t d[4];
+  cuuint64_t s[3];
+  cuuint32_t b[4], e[4] = {1u, 1u, 1u, 1u};
   for (int i = 0; i < rank; ++i) d[i] = (cuuint64_t)dims[i], b[i] = (cuuint32_t)box[i];
   for (int i = 0; i + 1 < rank; ++i) s[i] = (cuuint64_t)strides_elems[i] * 2;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -101,7 +101,7 @@ def test_v0_kernels_against_torch():
     z = torch.empty_like(x)
     call("lnx_se_scale", x.data_ptr(), gate.data_ptr(), z.data_ptr(), B, H * W, C, 0)
     assert float((z - x * torch.sigmoid(gate)[:, None, None, :]).abs().max()) < 1e-5
-    for hd, heads, N in ((48, 8, 53), (96, 8, 200), (64, 2, 17)):
+    for hd, heads, N in ((48, 8, 53), (96, 8, 200), (64, 2, 17), (48, 8, 200), (32, 4, 132), (16, 2, 240)):
         qkv = torch.randn(B, N, 3, heads, hd, device=DEV)
         bias = torch.randn(heads, N, N, device=DEV)
         o = torch.empty(B, N, heads * hd, device=DEV)
@@ -109,3 +109,9 @@ def test_v0_kernels_against_torch():
         q, k, v = qkv.permute(2, 0, 3, 1, 4)
         ref = (torch.softmax(q * hd ** -0.5 @ k.transpose(-2, -1) + bias, -1) @ v).transpose(1, 2).reshape(B, N, heads * hd)
         assert float((o - ref).abs().max()) < 2e-4
+        # bf16: head_dim <= 64 runs the tcgen05 kernel (TMA zero-fills the head dim up to 64), others the CUDA-core kernel
+        qb, ob = qkv.bfloat16(), torch.empty(B, N, heads * hd, device=DEV, dtype=torch.bfloat16)
+        call("lnx_attn_bias_fwd", qb.data_ptr(), bias.data_ptr(), ob.data_ptr(), B, heads, N, hd, hd ** -0.5, 1)
+        q, k, v = qb.float().permute(2, 0, 3, 1, 4)
+        refb = (torch.softmax(q * hd ** -0.5 @ k.transpose(-2, -1) + bias, -1) @ v).transpose(1, 2).reshape(B, N, heads * hd)
+        assert float((ob.float() - refb).abs().max() / refb.abs().max()) < 2e-2
