@@ -65,6 +65,7 @@ struct FwdParams {
 // barrier indices
 enum { KV_FULL = 0, KV_EMPTY = 2, Q_FULL = 4, Q_EMPTY = 6, S_FULL = 8, O_FULL = 10, T_EMPTY = 12, P_FULL = 14, P_EMPTY = 15, NBARS = 16 };
 
+template <bool BIAS>
 __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                                const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out,
                                                                float* __restrict__ lse, const FwdParams p) {
@@ -77,8 +78,8 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
   const int p_blocks = (p.nkp + 63) / 64;
   float* sMax = reinterpret_cast<float*>(sP + (size_t)p_blocks * 16384);  // [2 TMEM buffers][2 halves][128]
   float* sSum = sMax + 512;                                             // [2][2][128]
-  float* sBias = sSum + 512;                                            // [8 softmax warps][32 rows][17] (bias staging, when p.bias)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + (p.bias ? 8 * 32 * 17 : 0));
+  float* sBias = sSum + 512;                                            // [8 softmax warps][32 rows][17] (bias staging, BIAS only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + (BIAS ? 8 * 32 * 17 : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -182,13 +183,18 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
       float* bSum = sSum + buf * 256;
       mbar_wait(&bars[S_FULL + buf], ((uint32_t)t >> 1) & 1u);
       tcgen05_fence_after();
-      // logits = scale * S (+ bias).  The bias chunk [32 rows x 16 keys] of this warp is staged through shared memory with
-      // coalesced 16-byte loads (a lane owns one ROW, so direct loads would touch 32 cache lines per instruction).
-      const int j_ = t / p.n_qt, qt_ = t - j_ * p.n_qt;
-      const int bh_ = (int)blockIdx.x + j_ * (int)gridDim.x;
+      // logits = scale * S (+ bias), handled in the log2 domain.  BIAS: the [32 rows x 16 keys] bias chunk of this warp is
+      // staged through shared memory with coalesced 16-byte loads (a lane owns one ROW, so direct loads would touch 32
+      // cache lines per instruction).
       const float sl = p.scale * LOG2E;
       float* wb = sBias + sw * (32 * 17);
-      const float* bhead = p.bias ? p.bias + (long long)(bh_ % p.heads) * p.N * p.N : nullptr;
+      const float* bhead = nullptr;
+      int qt_ = 0;
+      if constexpr (BIAS) {
+        const int j_ = t / p.n_qt;
+        qt_ = t - j_ * p.n_qt;
+        bhead = p.bias + (long long)(((int)blockIdx.x + j_ * (int)gridDim.x) % p.heads) * p.N * p.N;
+      }
       auto stage_bias = [&](int c) {
         __syncwarp();
 #pragma unroll
@@ -202,19 +208,26 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
         }
         __syncwarp();
       };
-      // pass 1: row max over this half's valid keys (in the log2 domain)
+      // pass 1: row max over this half's valid keys
       float mx = -INFINITY;
       for (int c = c_begin; c < c_end; c += 16) {
         float v[16];
         tmem_ld16(trow + c, v);
-        if (bhead) stage_bias(c);
+        if constexpr (BIAS) {
+          stage_bias(c);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (c + i < p.N) {
-            float a = v[i] * sl;
-            if (bhead) a = fmaf(wb[lane * 17 + i], LOG2E, a);
-            mx = fmaxf(mx, a);
-          }
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sl, wb[lane * 17 + i] * LOG2E);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= sl;
+        }
+        if (c + 16 <= p.N) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c + i < p.N) mx = fmaxf(mx, v[i]);
         }
       }
       bMax[half * 128 + r] = mx;
@@ -227,15 +240,13 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
       for (int c = c_begin; c < c_end; c += 16) {
         float v[16];
         tmem_ld16(trow + c, v);
-        if (bhead) stage_bias(c);
+        if constexpr (BIAS) stage_bias(c);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float e = 0.f;
-          if (c + i < p.N) {
-            float a = fmaf(v[i], sl, -mxl);
-            if (bhead) a = fmaf(wb[lane * 17 + i], LOG2E, a);
-            e = ex2f(a);
-          }
+          float a = fmaf(v[i], sl, -mxl);
+          if constexpr (BIAS) a = fmaf(wb[lane * 17 + i], LOG2E, a);
+          float e = ex2f(a);
+          if (c + 16 > p.N && c + i >= p.N) e = 0.f;
           sum += e;
           v[i] = e;
         }
@@ -720,7 +731,7 @@ bool head_tmap(CUtensorMap* tm, const void* ptr, int BH, int N, int box_rows) {
   return make_tmap(tm, ptr, 3, dims, strides, box);
 }
 
-int g_fwd_smem_set = 0;  // largest dynamic shared-memory size attn_fwd_tc2_kernel has been configured for
+int g_fwd_smem_set = 0, g_fwd_bias_smem_set = 0;  // largest dynamic shared-memory size each attn_fwd_tc2_kernel variant was configured for
 
 }  // namespace
 
@@ -738,11 +749,11 @@ int lnx_attn_fwd_tc2(const void* q, const void* k, const void* v, void* out, flo
   const size_t smem = 1024 + 4 * (size_t)p.nkp * 128 + 2 * 16384 + (size_t)((p.nkp + 63) / 64) * 16384 + 8 * 128 * 4 + NBARS * 8 + 64;
   if (smem > 232448) return LNX_ERR_UNSUPPORTED;
   if ((int)smem > g_fwd_smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return lnx_set_cuda_error(e);
     g_fwd_smem_set = (int)smem;
   }
-  attn_fwd_tc2_kernel<<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tq, tk, tv, (bf16*)out, lse, p);
+  attn_fwd_tc2_kernel<false><<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tq, tk, tv, (bf16*)out, lse, p);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
@@ -773,12 +784,15 @@ int lnx_attn_bias_fwd_tc2(const void* qkv, const float* bias, void* out, int B, 
   const size_t smem = 1024 + 4 * (size_t)p.nkp * 128 + 2 * 16384 + (size_t)((p.nkp + 63) / 64) * 16384 + 8 * 128 * 4 + (bias ? 8 * 32 * 17 * 4 : 0) +
                       NBARS * 8 + 64;
   if (smem > 232448) return LNX_ERR_UNSUPPORTED;
-  if (smem > (size_t)g_fwd_smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int& set = bias ? g_fwd_bias_smem_set : g_fwd_smem_set;
+  if ((int)smem > set) {
+    cudaError_t e = bias ? cudaFuncSetAttribute(attn_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(attn_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return lnx_set_cuda_error(e);
-    g_fwd_smem_set = (int)smem;
+    set = (int)smem;
   }
-  attn_fwd_tc2_kernel<<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tm[0], tm[1], tm[2], (bf16*)out, nullptr, p);
+  if (bias) attn_fwd_tc2_kernel<true><<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tm[0], tm[1], tm[2], (bf16*)out, nullptr, p);
+  else attn_fwd_tc2_kernel<false><<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tm[0], tm[1], tm[2], (bf16*)out, nullptr, p);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
