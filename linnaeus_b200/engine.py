@@ -36,6 +36,8 @@ class TrainStep:
         self.weighting = LL.StaticTaskWeighting(self.keys, task_weights)
         self._graph = None
         self._static = None
+        self._stage = None
+        self._pending = False
         self.loss = None
 
     def _fwd_bwd(self, images, meta, targets: dict):
@@ -88,8 +90,49 @@ class TrainStep:
             self.opt.zero_grad()
         return loss
 
+    # ---- input pipelining ---------------------------------------------------
+    def prefetch(self, images, meta, targets: dict | None) -> None:
+        """Start the host->device copy of the NEXT step's inputs on a side stream (pinned host tensors), into staging
+        buffers, so it overlaps the graph of the step in flight; the next ``replay()`` waits for it, moves the staged
+        batch into the graph's static input buffers (device-to-device) and runs.  This is what a prefetching data
+        loader does for the reference's ``train.py`` loop (``non_blocking=True`` copies one batch ahead)."""
+        si, sm, st = self._static
+        if self._stage is None:
+            self._stage = (torch.empty_like(si), None if sm is None else torch.empty_like(sm), {k: torch.empty_like(v) for k, v in st.items()})
+            self._copy_stream = torch.cuda.Stream(device=si.device)
+            self._copy_done = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+        gi, gm, gt = self._stage
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)  # the previous staged batch has been moved into the static buffers
+        with torch.cuda.stream(cs):
+            gi.copy_(images, non_blocking=True)
+            if gm is not None and meta is not None:
+                gm.copy_(meta, non_blocking=True)
+            if targets is not None:
+                for k, v in targets.items():
+                    gt[k].copy_(v, non_blocking=True)
+            self._copy_done.record(cs)
+        self._pending = True
+
+    def _consume_prefetch(self) -> None:
+        si, sm, st = self._static
+        gi, gm, gt = self._stage
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copy_done)
+        si.copy_(gi, non_blocking=True)
+        if sm is not None:
+            sm.copy_(gm, non_blocking=True)
+        for k in st:
+            st[k].copy_(gt[k], non_blocking=True)
+        self._stage_free.record(cur)
+        self._pending = False
+
     def replay(self, images=None, meta=None, targets: dict | None = None) -> torch.Tensor:
         si, sm, st = self._static
+        if self._pending:
+            self._consume_prefetch()
         if images is not None:
             si.copy_(images, non_blocking=True)
         if meta is not None and sm is not None:
