@@ -198,6 +198,13 @@ int lnx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr,
  * OverlapPatchEmbed.proj (R/models/blocks/relative_mhsa.py:57-66); the contraction runs on lnx_gemm. */
 int lnx_im2col3x3(const void* x, int x_is_nchw_f32, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo, int Kpad, int dtype,
                   lnx_stream_t s);
+/* Dense 3x3 convolution, stride 1, pad 1, as an implicit GEMM on the tensor cores (no im2col buffer): x [B,H,W,C] bf16
+ * (C <= 64, C % 8 == 0), w9 [N, 9*64] bf16 (per output channel: 9 taps x 64 input channels, zero padded), bias float[N]
+ * (nullable; the folded BatchNorm shift), optional ReLU, y [B,H,W,N] bf16 (N % 16 == 0; the 9 weight tiles stay resident in
+ * shared memory, which bounds N at 96).  The stem convs 2 and 3
+ * of mFormerV0 (R/models/mFormerV0.py:175-190).  Returns LNX_ERR_UNSUPPORTED for other shapes / dtypes. */
+int lnx_conv3x3_s1(const void* x, const void* w9, const float* bias, void* y, int B, int H, int W, int C, int N, int relu, int dtype,
+                   lnx_stream_t s);
 /* nn.MaxPool2d(3, 2, 1) on NHWC (R/models/mFormerV0.py:193). */
 int lnx_maxpool3s2(const void* x, void* y, int B, int H, int W, int C, int dtype, lnx_stream_t s);
 /* Depthwise 3x3 with explicit top/left padding (TF "same" static padding of Conv2dStaticSamePadding,

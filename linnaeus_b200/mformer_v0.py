@@ -271,6 +271,10 @@ class mFormerV0(nn.Module):
             if kp != w2d.shape[1]:
                 w2d = TF.pad(w2d, (0, kp - w2d.shape[1]))
             f[name] = (w2d.contiguous().to(cd), b.float().contiguous())
+            if cd == torch.bfloat16 and conv.stride[0] == 1 and w.shape[1] <= 64 and w.shape[1] % 8 == 0 and w.shape[0] % 16 == 0 and w.shape[0] <= 96:
+                # implicit-GEMM layout (lnx_conv3x3_s1): per output channel 9 taps x 64 input channels, zero padded
+                w9 = TF.pad(w.permute(0, 2, 3, 1), (0, 64 - w.shape[1])).reshape(w.shape[0], 9 * 64)
+                f[name + ".w9"] = w9.contiguous().to(cd)
 
         def conv1(name, conv, bn):
             w = conv.weight.detach().flatten(1)
@@ -309,9 +313,14 @@ class mFormerV0(nn.Module):
         return f
 
     # -- forward -----------------------------------------------------------------
-    def _conv3x3(self, x, wb, B, H, W, C, stride, act, cd, image=False):
+    def _conv3x3(self, x, wb, B, H, W, C, stride, act, cd, image=False, w9=None):
         w2d, b = wb
         Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+        if w9 is not None and stride == 1 and not image and act in (None, "relu"):
+            # tensor-core implicit GEMM straight from the NHWC activation (no im2col buffer)
+            y = torch.empty((B * H * W, w9.shape[0]), dtype=cd, device=x.device)
+            call("lnx_conv3x3_s1", x.data_ptr(), w9.data_ptr(), b.data_ptr(), y.data_ptr(), B, H, W, C, w9.shape[0], int(act == "relu"), dt(y))
+            return y, H, W
         a = torch.empty((B * Ho * Wo, w2d.shape[1]), dtype=cd, device=x.device)
         call("lnx_im2col3x3", x.data_ptr(), int(image), a.data_ptr(), B, H, W, C, stride, Ho, Wo, w2d.shape[1], dt(a))
         y = F.linear(a, w2d, b, weight_c=w2d, act=act)
@@ -377,9 +386,9 @@ class mFormerV0(nn.Module):
             x = x.float().contiguous()
             y, H, W = self._conv3x3(x, f["stem0"], B, Hi, Wi, Cin, 2, "relu", cd, image=True)
             c = f["stem0"][0].shape[0]
-            y, H, W = self._conv3x3(y, f["stem1"], B, H, W, c, 1, "relu", cd)
+            y, H, W = self._conv3x3(y, f["stem1"], B, H, W, c, 1, "relu", cd, w9=f.get("stem1.w9"))
             c = f["stem1"][0].shape[0]
-            y, H, W = self._conv3x3(y, f["stem2"], B, H, W, c, 1, "relu", cd)
+            y, H, W = self._conv3x3(y, f["stem2"], B, H, W, c, 1, "relu", cd, w9=f.get("stem2.w9"))
             c = f["stem2"][0].shape[0]
             Hp, Wp = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
             z = torch.empty((B * Hp * Wp, c), dtype=cd, device=x.device)

@@ -115,3 +115,27 @@ def test_v0_kernels_against_torch():
         q, k, v = qb.float().permute(2, 0, 3, 1, 4)
         refb = (torch.softmax(q * hd ** -0.5 @ k.transpose(-2, -1) + bias, -1) @ v).transpose(1, 2).reshape(B, N, heads * hd)
         assert float((ob.float() - refb).abs().max() / refb.abs().max()) < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C,N,relu", [(2, 16, 32, 64, 64, 1), (3, 112, 112, 48, 64, 1), (1, 13, 21, 64, 96, 0), (2, 8, 16, 16, 32, 1),
+                                            (1, 24, 40, 32, 48, 0)])
+def test_conv3x3_implicit_gemm(B, H, W, C, N, relu):
+    """lnx_conv3x3_s1 (TMA-shifted windows + tcgen05, zero-filled borders / channels) against F.conv2d of the same bf16 data."""
+    import torch.nn.functional as TF
+
+    from linnaeus_b200._lib import call
+
+    torch.manual_seed(C + N)
+    torch.backends.cudnn.allow_tf32 = False
+    x = torch.randn(B, H, W, C, device=DEV).bfloat16()
+    w = (torch.randn(N, C, 3, 3, device=DEV) / (3 * C ** 0.5)).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    w9 = TF.pad(w.permute(0, 2, 3, 1), (0, 64 - C)).reshape(N, 9 * 64).contiguous()
+    y = torch.empty(B, H, W, N, device=DEV, dtype=torch.bfloat16)
+    call("lnx_conv3x3_s1", x.data_ptr(), w9.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, C, N, relu, 1)
+    ref = TF.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, 1, 1)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    assert float((y.float() - ref).abs().max() / ref.abs().max()) < 1e-2
