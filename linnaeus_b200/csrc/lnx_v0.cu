@@ -154,16 +154,17 @@ __global__ void dwconv3_kernel(const T* __restrict__ x, const float* __restrict_
         else zero16(col[dh]);
       }
     };
-    Vec16<T> win[3][3];  // [column][row]
+    // win = the three input columns of the current output; pre = the column(s) the NEXT output adds, loaded one
+    // iteration ahead so the global-load latency overlaps the 72 FMAs + swish of the current pixel
+    Vec16<T> win[3][3], pre[STRIDE][3];  // [column][row]
     load_col(-pad_l, win[0]);
-    if (STRIDE == 1) load_col(1 - pad_l, win[1]);
+    load_col(1 - pad_l, win[1]);
+    load_col(2 - pad_l, win[2]);
     for (int wo = 0; wo < Wo; ++wo) {
       const int w0 = wo * STRIDE - pad_l;
-      if (STRIDE == 1) {
-        load_col(w0 + 2, win[2]);
-      } else {
-        load_col(w0 + 1, win[1]);
-        load_col(w0 + 2, win[2]);
+      if (wo + 1 < Wo) {
+#pragma unroll
+        for (int k = 0; k < STRIDE; ++k) load_col(w0 + 3 + k, pre[k]);
       }
       float acc[V];
 #pragma unroll
@@ -183,15 +184,17 @@ __global__ void dwconv3_kernel(const T* __restrict__ x, const float* __restrict_
         psum[e] += o.get(e);  // pool what the next layer will read (the rounded value)
       }
       st16(y + ((b * Ho + ho) * (long long)Wo + wo) * C + c0, o);
-      if (STRIDE == 1) {
 #pragma unroll
-        for (int dh = 0; dh < 3; ++dh) {
+      for (int dh = 0; dh < 3; ++dh) {
+        if (STRIDE == 1) {
           win[0][dh] = win[1][dh];
           win[1][dh] = win[2][dh];
+          win[2][dh] = pre[0][dh];
+        } else {
+          win[0][dh] = win[2][dh];
+          win[1][dh] = pre[0][dh];
+          win[2][dh] = pre[STRIDE - 1][dh];
         }
-      } else {
-#pragma unroll
-        for (int dh = 0; dh < 3; ++dh) win[0][dh] = win[2][dh];
       }
     }
   }
