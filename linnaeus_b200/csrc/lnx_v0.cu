@@ -213,19 +213,132 @@ __global__ void dwconv3_kernel(const T* __restrict__ x, const float* __restrict_
   }
 }
 
-// ---------------------------------------------------------------- x * sigmoid(gate[b, c])
-template <typename T>
-__global__ void se_scale_kernel(const T* __restrict__ x, const float* __restrict__ gate, T* __restrict__ y, long long B, int HW, int C) {
-  constexpr int V = Vec16<T>::N;
-  const int cv = C / V;
-  const long long total = B * HW * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv);
-    const long long b = i / ((long long)cv * HW);
-    Vec16<T> v = ld16(x + i * V);
+// bf16 fast path.  The kernel above holds 8 channels x (9 taps + 9 window vectors) per thread = 177+ registers, one
+// 192-thread block per SM, so HBM latency is exposed.  Here a lane owns ONE channel pair (a 32-bit load = both
+// channels of a pixel, one packed fp32x2 FMA = both channels of a tap, lnx_dwconv_bf16.cu has the rationale) and
+// R consecutive output rows: the window is (R-1)*STRIDE+3 input rows x 3 columns of already unpacked float2, the
+// next column is loaded one iteration ahead as raw words, and each input row is read from L1/L2 (R+2)/R times
+// instead of 3.  ~100 registers -> five 128-thread blocks per SM; a warp reads / writes 128 contiguous bytes per
+// pixel.  Pool partials are folded over the block's row slots in shared memory, then one coalesced atomic per
+// (block, channel).
+template <int STRIDE, int R>
+__global__ void __launch_bounds__(128, 5)
+    dwconv3_x2_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c, const float* __restrict__ scale, const float* __restrict__ shift,
+                      bf16* __restrict__ y, float* __restrict__ pool_sum, int H, int W, int C, int pad_t, int pad_l, int Ho, int Wo, int act) {
+  constexpr int NR = (R - 1) * STRIDE + 3;
+  extern __shared__ float s_pool[];  // [blockDim.y][2 * blockDim.x] when pool_sum
+  const int c0 = (blockIdx.z * blockDim.x + threadIdx.x) * 2;
+  const long long b = blockIdx.y;
+  const int ho0 = (blockIdx.x * blockDim.y + threadIdx.y) * R;
+  float2 wr[9];
 #pragma unroll
-    for (int e = 0; e < V; ++e) v.set(e, v.get(e) / (1.f + expf(-gate[b * C + c * V + e])));
-    st16(y + i * V, v);
+  for (int t = 0; t < 9; ++t) wr[t] = *reinterpret_cast<const float2*>(w9c + t * C + c0);
+  const float2 sc = scale ? *reinterpret_cast<const float2*>(scale + c0) : make_float2(1.f, 1.f);
+  const float2 sh = shift ? *reinterpret_cast<const float2*>(shift + c0) : make_float2(0.f, 0.f);
+  float2 psum = make_float2(0.f, 0.f);
+  if (ho0 < Ho) {
+    const int hbase = ho0 * STRIDE - pad_t;
+    const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + b * (long long)H * W * C + c0);
+    const int rs = W * (C / 2), ps = C / 2;  // row / pixel strides in 32-bit words
+    unsigned rowmask = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+      if (hbase + r >= 0 && hbase + r < H) rowmask |= 1u << r;
+    auto load_col = [&](int w, uint32_t* col) {
+      const bool wok = w >= 0 && w < W;
+      const uint32_t* p = xb + (long long)hbase * rs + (long long)w * ps;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) col[r] = (wok && ((rowmask >> r) & 1u)) ? __ldg(p + (long long)r * rs) : 0u;
+    };
+    auto unpack = [](uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); };
+    float2 win[3][NR];       // [column slot][row]; slot (wo + dw) % 3 holds input column wo * STRIDE - pad_l + dw (stride 1)
+    uint32_t pre[STRIDE][NR];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      load_col(k - pad_l, pre[0]);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) win[k][r] = unpack(pre[0][r]);
+    }
+    bf16* yb = y + ((b * Ho + ho0) * (long long)Wo) * C + c0;
+    for (int wo3 = 0; wo3 < Wo; wo3 += 3) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int wo = wo3 + u;
+        if (wo < Wo) {
+          const int w0 = wo * STRIDE - pad_l;
+          if (wo + 1 < Wo) {
+#pragma unroll
+            for (int k = 0; k < STRIDE; ++k) load_col(w0 + 3 + k, pre[k]);
+          }
+          // column slots of this output: stride 1 rotates one slot per output, stride 2 two slots per output
+          const int s0 = (u * STRIDE) % 3, s1 = (u * STRIDE + 1) % 3, s2 = (u * STRIDE + 2) % 3;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (ho0 + r < Ho) {
+              float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int dh = 0; dh < 3; ++dh) {
+                acc = __ffma2_rn(win[s0][r * STRIDE + dh], wr[dh * 3 + 0], acc);
+                acc = __ffma2_rn(win[s1][r * STRIDE + dh], wr[dh * 3 + 1], acc);
+                acc = __ffma2_rn(win[s2][r * STRIDE + dh], wr[dh * 3 + 2], acc);
+              }
+              acc = __ffma2_rn(acc, sc, sh);
+              if (act == 1) {
+                acc.x = swish_fast(acc.x);
+                acc.y = swish_fast(acc.y);
+              }
+              const __nv_bfloat162 o = __floats2bfloat162_rn(acc.x, acc.y);
+              const uint32_t ow = *reinterpret_cast<const uint32_t*>(&o);
+              *reinterpret_cast<uint32_t*>(yb + ((long long)r * Wo + wo) * C) = ow;
+              const float2 of = unpack(ow);  // pool what the next layer will read (the rounded value)
+              psum.x += of.x;
+              psum.y += of.y;
+            }
+          }
+          // retire the oldest column(s): the slots the next output no longer needs take the prefetched columns
+#pragma unroll
+          for (int k = 0; k < STRIDE; ++k) {
+            const int slot = (u * STRIDE + k) % 3;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) win[slot][r] = unpack(pre[k][r]);
+          }
+        }
+      }
+    }
+  }
+  if (pool_sum) {
+    const int tx2 = 2 * blockDim.x;
+    s_pool[threadIdx.y * tx2 + 2 * threadIdx.x] = psum.x;
+    s_pool[threadIdx.y * tx2 + 2 * threadIdx.x + 1] = psum.y;
+    __syncthreads();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int i = tid; i < tx2; i += blockDim.x * blockDim.y) {
+      float t = 0.f;
+      for (int r = 0; r < (int)blockDim.y; ++r) t += s_pool[r * tx2 + i];
+      atomicAdd(pool_sum + b * C + blockIdx.z * tx2 + i, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- x * sigmoid(gate[b, c])
+// grid (pixel chunks, B); block (C / V, rows): a thread owns one channel vector, evaluates its V sigmoids once and streams
+// the chunk's pixels through them (one 16-byte load, V multiplies, one 16-byte store per pixel).
+template <typename T>
+__global__ void se_scale_kernel(const T* __restrict__ x, const float* __restrict__ gate, T* __restrict__ y, int HW, int C, int chunk) {
+  constexpr int V = Vec16<T>::N;
+  const long long b = blockIdx.y;
+  const int c0 = threadIdx.x * V;
+  float g[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) g[e] = 1.f / (1.f + expf(-gate[b * C + c0 + e]));
+  const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+  const long long base = b * HW * (long long)C + c0;
+#pragma unroll 4
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    Vec16<T> v = ld16(x + base + (long long)p * C);
+#pragma unroll
+    for (int e = 0; e < V; ++e) v.set(e, v.get(e) * g[e]);
+    st16(y + base + (long long)p * C, v);
   }
 }
 
@@ -346,17 +459,34 @@ extern "C" int lnx_dwconv3_fwd(const void* x, const float* w9c, const float* sca
   const int V = dtype == LNX_F32 ? 4 : 8;
   LNX_REQUIRE(dtype == LNX_F32 || dtype == LNX_BF16, LNX_ERR_DTYPE);
   LNX_REQUIRE(C % V == 0 && C / V <= 1024, LNX_ERR_SHAPE);
+  cudaStream_t st = (cudaStream_t)s;
+  if (dtype == LNX_BF16) {  // channel-pair kernel (FFMA2)
+    const int cp = C / 2;
+    int tx = 0;
+    for (int d = 128; d >= 1 && !tx; --d)
+      if (cp % d == 0 && (d % 32 == 0 || d == cp)) tx = d;
+    if (!tx)
+      for (int d = 128; d >= 1 && !tx; --d)
+        if (cp % d == 0) tx = d;
+    const int R = stride == 1 ? 4 : 2;
+    const int slots = (Ho + R - 1) / R;
+    int ty = max(1, min(128 / tx, slots));
+    while (ty > 1 && ((slots + ty - 1) / ty) * ty - slots > slots / 8) --ty;
+    dim3 grid((slots + ty - 1) / ty, B, cp / tx), block(tx, ty);
+    const size_t smem = pool_sum ? (size_t)ty * 2 * tx * sizeof(float) : 0;
+    if (stride == 1)
+      dwconv3_x2_kernel<1, 4><<<grid, block, smem, st>>>((const bf16*)x, w9c, scale, shift, (bf16*)y, pool_sum, H, W, C, pad_t, pad_l, Ho, Wo, act);
+    else
+      dwconv3_x2_kernel<2, 2><<<grid, block, smem, st>>>((const bf16*)x, w9c, scale, shift, (bf16*)y, pool_sum, H, W, C, pad_t, pad_l, Ho, Wo, act);
+    LNX_CHECK_LAUNCH();
+    return LNX_OK;
+  }
   const int tx = C / V;
   const int ty = max(1, min(8, 256 / tx));
   dim3 grid((Ho + ty - 1) / ty, B), block(tx, ty);
   const size_t smem = pool_sum ? (size_t)ty * C * sizeof(float) : 0;
-  cudaStream_t st = (cudaStream_t)s;
 #define LNX_DW3(T, S) dwconv3_kernel<T, S><<<grid, block, smem, st>>>((const T*)x, w9c, scale, shift, (T*)y, pool_sum, H, W, C, pad_t, pad_l, Ho, Wo, act)
-  if (dtype == LNX_F32) {
-    if (stride == 1) LNX_DW3(float, 1); else LNX_DW3(float, 2);
-  } else {
-    if (stride == 1) LNX_DW3(bf16, 1); else LNX_DW3(bf16, 2);
-  }
+  if (stride == 1) LNX_DW3(float, 1); else LNX_DW3(float, 2);
 #undef LNX_DW3
   LNX_CHECK_LAUNCH();
   return LNX_OK;
@@ -367,14 +497,17 @@ extern "C" int lnx_se_scale(const void* x, const float* gate, void* y, int B, in
   LNX_REQUIRE(B > 0 && HW > 0 && C > 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(y), LNX_ERR_ALIGN);
   cudaStream_t st = (cudaStream_t)s;
-  if (dtype == LNX_F32) {
-    LNX_REQUIRE(C % 4 == 0, LNX_ERR_SHAPE);
-    se_scale_kernel<float><<<grid_for((long long)B * HW * (C / 4), 256), 256, 0, st>>>((const float*)x, gate, (float*)y, B, HW, C);
-  } else if (dtype == LNX_BF16) {
-    LNX_REQUIRE(C % 8 == 0, LNX_ERR_SHAPE);
-    se_scale_kernel<bf16><<<grid_for((long long)B * HW * (C / 8), 256), 256, 0, st>>>((const bf16*)x, gate, (bf16*)y, B, HW, C);
-  } else
-    return LNX_ERR_DTYPE;
+  LNX_REQUIRE(dtype == LNX_F32 || dtype == LNX_BF16, LNX_ERR_DTYPE);
+  const int V = dtype == LNX_F32 ? 4 : 8;
+  LNX_REQUIRE(C % V == 0 && C / V <= 1024 && B <= 65535, LNX_ERR_SHAPE);
+  const int tx = C / V, ty = max(1, 256 / tx);
+  // ~8 chunks per SM over the whole batch, at least 4 pixels per thread
+  int chunks = max(1, min((HW + 4 * ty - 1) / (4 * ty), (8 * kNumSMs + B - 1) / B));
+  const int chunk = (HW + chunks - 1) / chunks;
+  chunks = (HW + chunk - 1) / chunk;
+  dim3 grid(chunks, B), block(tx, ty);
+  if (dtype == LNX_F32) se_scale_kernel<float><<<grid, block, 0, st>>>((const float*)x, gate, (float*)y, HW, C, chunk);
+  else se_scale_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, gate, (bf16*)y, HW, C, chunk);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
