@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 FWD_GFLOP = {"sm": 8.659, "md": 12.505, "xl": 448.16}  # per image (SURVEY.md section 6, 224^2; xl at 384^2)
 FWD_GFLOP_V0 = {"sm": 8.94}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (profiles/r01_kernels_summary.md),
-# keyed by (variant, per-GPU batch, image size, dtype); None when that exact shape was not captured
-NCU_TRAFFIC_BYTES = {}
+# keyed by (arch, variant, per-GPU batch, image size, dtype); None when that exact shape was not captured
+NCU_TRAFFIC_BYTES = {("v1", "sm", 256, 224, "bf16"): 154.3e6 + 1175.4e6}  # rows 0-1 of r01_kernels_summary.md
 
 
 def parse():
@@ -372,7 +372,7 @@ def run_b200(args):
     kms, _ = timed(gemm, 20, 3)
     alg_bytes = (M * K + N * K + n_out * M * N) * esz
     ach = alg_bytes / (kms / 1e3) / 1e9
-    traffic = NCU_TRAFFIC_BYTES.get((args.variant, B, S, args.dtype))
+    traffic = NCU_TRAFFIC_BYTES.get((args.arch, args.variant, B, S, args.dtype))
     gflop = (FWD_GFLOP_V0 if args.arch == "v0" else FWD_GFLOP).get(args.variant, 0.0)
     roofline = {"bound": "hbm", "kernel": kname % (M, K, N),
                 "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "peak_source": peak_src,

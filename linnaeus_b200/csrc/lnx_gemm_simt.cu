@@ -125,8 +125,90 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs g, int k_
   }
 }
 
+
+// ---- skinny shapes (the metadata heads: Linear(2 / 3 / 10 -> D) on a [B, 15] fp32 tensor).  The 128 x 128 tile above
+// spends ~45 us on them (one serial k-step, a 97 % empty tile, 64 dependent bias-load/store pairs per thread); these two
+// kernels are plain per-output loops.
+// C[m, n..n+3] = epilogue(sum_k A[m, k] * B[n, k]), K <= 16, no transposes
+template <typename TA, typename TC>
+__global__ void __launch_bounds__(256) gemm_small_k_kernel(const GemmArgs g) {
+  const int n4 = (g.N + 3) / 4;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)g.M * n4) return;
+  const int m = (int)(t / n4), n0 = (int)(t % n4) * 4;
+  const TA* a = reinterpret_cast<const TA*>(g.A) + (long long)m * g.lda;
+  const TA* b = reinterpret_cast<const TA*>(g.B) + (long long)n0 * g.ldb;
+  float av[16], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 16; ++k) av[k] = k < g.K ? to_f32(a[k]) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (n0 + j < g.N) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k < g.K) acc[j] = fmaf(av[k], to_f32(b[(long long)j * g.ldb + k]), acc[j]);
+    }
+  }
+  TC* C = reinterpret_cast<TC*>(g.C);
+  TC* aux = reinterpret_cast<TC*>(g.aux_out);
+  const TC* agi = reinterpret_cast<const TC*>(g.act_grad_in);
+  const TC* res = reinterpret_cast<const TC*>(g.residual);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (n0 + j < g.N) {
+      const long long idx = (long long)m * g.N + n0 + j;
+      C[idx] = from_f32<TC>(gemm_epilogue_scalar<TC>(acc[j], m, n0 + j, idx, g, aux, agi, res));
+    }
+  }
+}
+
+// C[m, n] (+)= sum_k A[k, m] * B[k, n], N <= 16, both operands "transposed" (the weight gradient dy^T x of a skinny Linear):
+// a thread owns one m (coalesced reads of A across the block), the K range is split over blockIdx.y and added with atomics
+template <typename TA>
+__global__ void __launch_bounds__(128) gemm_skinny_n_kernel(const GemmArgs g, int k_per_split, int atomic) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kbeg = blockIdx.y * k_per_split, kend = min(g.K, kbeg + k_per_split);
+  if (m >= g.M) return;
+  const TA* A = reinterpret_cast<const TA*>(g.A) + m;
+  const TA* B = reinterpret_cast<const TA*>(g.B);
+  float acc[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+#pragma unroll 4
+  for (int k = kbeg; k < kend; ++k) {
+    const float a = to_f32(A[(long long)k * g.lda]);
+#pragma unroll
+    for (int n = 0; n < 16; ++n)
+      if (n < g.N) acc[n] = fmaf(a, to_f32(B[(long long)k * g.ldb + n]), acc[n]);
+  }
+  float* C = reinterpret_cast<float*>(g.C) + (long long)m * g.N;
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    if (n < g.N) {
+      if (atomic) atomicAdd(C + n, acc[n]);
+      else C[n] = acc[n];
+    }
+  }
+}
+
 template <typename TA, typename TC>
 int launch(const GemmArgs& g, cudaStream_t st) {
+  if (!g.a_trans && !g.b_trans && g.K <= 16 && !g.accumulate) {
+    const long long total = (long long)g.M * ((g.N + 3) / 4);
+    gemm_small_k_kernel<TA, TC><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g);
+    LNX_CHECK_LAUNCH();
+    return LNX_OK;
+  }
+  if (g.a_trans && g.b_trans && g.N <= 16 && sizeof(TC) == 4 && !g.bias && !g.act && !g.aux_out && !g.act_grad_in && !g.residual &&
+      !g.col_scale && !g.row_scale) {
+    const int bx = (g.M + 127) / 128;
+    int splits = g.accumulate ? max(1, min((g.K + 31) / 32, (kNumSMs + bx - 1) / bx)) : 1;
+    const int kps = (g.K + splits - 1) / splits;
+    splits = (g.K + kps - 1) / kps;
+    gemm_skinny_n_kernel<TA><<<dim3(bx, splits), 128, 0, st>>>(g, kps, g.accumulate);
+    LNX_CHECK_LAUNCH();
+    return LNX_OK;
+  }
   const int gx = (g.N + BN - 1) / BN, gy = (g.M + BM - 1) / BM;
   int splits = 1;
   if (g.accumulate) {

@@ -131,6 +131,29 @@ def test_gemm_simt_epilogue_and_accumulate(dtype):
         F.FORCE_SIMT = False
 
 
+@pytest.mark.parametrize("K,N", [(2, 384), (3, 96), (10, 768), (16, 50)])
+def test_skinny_linear_paths(K, N):
+    """The metadata-head Linear(K <= 16): fp32 columns of a pitched [B, 15] tensor, bias + ReLU epilogue, bf16 output, and its
+    weight gradient dy^T x accumulated into an existing dW (R/models/utils.py metadata heads)."""
+    F = _F()
+    Bsz, pitch = 257, 17
+    meta = torch.randn(Bsz, pitch, device=DEV)
+    x = meta[:, 1:1 + K]
+    w = torch.randn(N, K, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    ref = torch.relu(x @ w.t() + bias)
+    for od, t in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
+        out = F.gemm(x, w, Bsz, N, K, lda=pitch, out_dtype=od, bias=bias, act=2)
+        assert rel_err(out, ref) < t
+    dy = torch.randn(Bsz, N, device=DEV)
+    dw0 = torch.randn(N, K, device=DEV)
+    dw = dw0.clone()
+    F.wgrad(dy, x, x_ld=pitch, out=dw)
+    torch.testing.assert_close(dw, dw0 + dy.t() @ x, rtol=1e-5, atol=1e-4)
+    plain = F.gemm(dy, x, N, K, Bsz, a_trans=True, b_trans=True, lda=N, ldb=pitch, out_dtype=torch.float32)
+    torch.testing.assert_close(plain, dy.t() @ x, rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_layout_kernels(dtype):
     F = _F()
