@@ -53,11 +53,12 @@ __global__ void rope_table_kernel(const float* __restrict__ freqs, float* __rest
   }
 }
 
-// CTA = TOK consecutive tokens; thread = (token, which in {q,k,v}, head, 8-element chunk): no per-element index
-// divisions, 16-byte coalesced reads of the [B*N, 3*heads*hd] rows, 128-byte segments on the head-major side.
-template <typename T, int TOK>
+// CTA = TOK * ITER consecutive tokens; thread = (token slot, which in {q,k,v}, head, 8-element chunk) and walks ITER tokens
+// TOK apart: the index decomposition is done once, the only division is 32-bit, all ITER 16-byte row reads are issued before
+// the first use; coalesced reads of the [B*N, 3*heads*hd] rows, 128-byte segments on the head-major side.
+template <typename T, int TOK, int ITER>
 __global__ void rope_qk_fwd_kernel(const T* __restrict__ qkv, const float* __restrict__ cos_tab, T* __restrict__ q, T* __restrict__ k,
-                                   T* __restrict__ v, long long BN, int N, int heads, int hd, int n_extra, float q_scale) {
+                                   T* __restrict__ v, unsigned BN, int N, int heads, int hd, int n_extra, float q_scale) {
   const int chunks = hd / 8;
   const int per_tok = 3 * heads * chunks;
   const int t = threadIdx.x;
@@ -67,26 +68,39 @@ __global__ void rope_qk_fwd_kernel(const T* __restrict__ qkv, const float* __res
   const int ch = w % chunks;
   const int h = (w / chunks) % heads;
   const int which = w / (chunks * heads);
-  const long long row = (long long)blockIdx.x * TOK + tok;  // = b * N + n
-  if (row >= BN) return;
-  const long long b = row / N;
-  const int n = (int)(row - b * N);
-  float x[8];
-  ld8<T>(qkv + row * (long long)per_tok * 8 + (long long)w * 8, x);
-  if (which < 2) {
-    const float sc = (which == 0) ? q_scale : 1.0f;
-    if (n >= n_extra) {
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(cos_tab + ((long long)(n - n_extra) * heads + h) * (hd / 2) + ch * 4));
-      const float ct[4] = {c4.x * sc, c4.y * sc, c4.z * sc, c4.w * sc};
+  const unsigned row0 = blockIdx.x * (unsigned)(TOK * ITER) + tok;  // = b * N + n
+  const float sc = (which == 0) ? q_scale : 1.0f;
+  T* const dst0 = (which == 0 ? q : which == 1 ? k : v) + (long long)h * N * hd + ch * 8;
+  float x[ITER][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] *= ct[e >> 1];
-    } else {
+  for (int it = 0; it < ITER; ++it) {
+    const unsigned row = row0 + it * TOK;
+    if (row < BN) ld8<T>(qkv + ((long long)row * per_tok + w) * 8, x[it]);
+  }
+  unsigned b = row0 / (unsigned)N;
+  int n = (int)(row0 - b * (unsigned)N);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] *= sc;
+  for (int it = 0; it < ITER; ++it) {
+    if (row0 + it * TOK < BN) {
+      if (which < 2) {
+        if (n >= n_extra) {
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(cos_tab + ((long long)(n - n_extra) * heads + h) * (hd / 2) + ch * 4));
+          const float ct[4] = {c4.x * sc, c4.y * sc, c4.z * sc, c4.w * sc};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[it][e] *= ct[e >> 1];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[it][e] *= sc;
+        }
+      }
+      st8<T>(dst0 + ((long long)b * heads * N + n) * hd, x[it]);
+    }
+    n += TOK;
+    while (n >= N) {
+      n -= N;
+      ++b;
     }
   }
-  T* dst = (which == 0 ? q : which == 1 ? k : v) + (((b * heads + h) * N + n) * hd) + ch * 8;
-  st8<T>(dst, x);
 }
 
 // grid: (N, batch chunks); thread = (which in {q,k,v}, head, pair-chunk of 4 pairs)
@@ -177,9 +191,10 @@ extern "C" int lnx_rope_qk_fwd(const void* qkv, const float* cos_tab, void* q, v
   LNX_REQUIRE(per_tok <= 1024 && hd % 8 == 0 && (hd / 2) % 4 == 0, LNX_ERR_UNSUPPORTED);
   const long long BN = (long long)B * N;
   cudaStream_t st = (cudaStream_t)s;
+  LNX_REQUIRE(BN < (1LL << 31), LNX_ERR_SHAPE);
 #define LNX_ROPE_F(T, TOK)                                                                                                         \
-  rope_qk_fwd_kernel<T, TOK><<<(unsigned)((BN + TOK - 1) / TOK), ((per_tok * TOK + 31) / 32) * 32, 0, st>>>(                         \
-      (const T*)qkv, cos_tab, (T*)q, (T*)k, (T*)v, BN, N, heads, hd, n_extra, q_scale)
+  rope_qk_fwd_kernel<T, TOK, 4><<<(unsigned)((BN + TOK * 4 - 1) / (TOK * 4)), ((per_tok * TOK + 31) / 32) * 32, 0, st>>>(            \
+      (const T*)qkv, cos_tab, (T*)q, (T*)k, (T*)v, (unsigned)BN, N, heads, hd, n_extra, q_scale)
   if (dtype == LNX_F32) {
     if (per_tok * 4 <= 1024) LNX_ROPE_F(float, 4); else LNX_ROPE_F(float, 1);
   } else if (dtype == LNX_BF16) {
@@ -199,9 +214,21 @@ extern "C" int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, c
   LNX_REQUIRE(lnx_aligned16(dq) && lnx_aligned16(dk) && lnx_aligned16(dv) && lnx_aligned16(qkv) && lnx_aligned16(dqkv), LNX_ERR_ALIGN);
   const int work = 3 * heads * (hd / 8);
   const int threads = min(256, ((work + 31) / 32) * 32);
-  int by = max(1, min(B, (kNumSMs * 8 + N - 1) / N));
-  const int bpb = (B + by - 1) / by;
-  by = (B + bpb - 1) / bpb;
+  // batch chunk per CTA: the grid (N x chunks) should fill whole waves of resident CTAs (6 per SM at 64 registers x 160
+  // threads) - the old fixed N x 6 grid ran as 1.35 waves; among chunkings with >= 2 waves take the one wasting the least
+  // of its last wave, preferring larger chunks (fewer dtheta atomics)
+  const double slots = 6.0 * kNumSMs;
+  int bpb = B;
+  double best = -1.0;
+  for (int c = B; c >= 1; --c) {
+    const int chunks_c = (B + c - 1) / c;
+    const double waves = (double)N * chunks_c / slots;
+    if (waves < 2.0 && c > 1) continue;
+    const double eff = waves / ceil(waves);
+    if (eff > best + 0.02) best = eff, bpb = c;
+    if (waves > 12.0) break;
+  }
+  const int by = (B + bpb - 1) / bpb;
   dim3 grid(N, by);
   cudaStream_t st = (cudaStream_t)s;
   if (dtype == LNX_F32)
