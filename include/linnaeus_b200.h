@@ -218,6 +218,25 @@ int lnx_se_scale(const void* x, const float* gate, void* y, int B, int HW, int C
  * (RelativeAttention.forward, R/models/blocks/relative_mhsa.py:201-236); bias float [heads, N, N] or NULL. */
 int lnx_attn_bias_fwd(const void* qkv, const float* bias, void* out, int B, int heads, int N, int hd, float scale, int dtype, lnx_stream_t s);
 
+
+/* ---- validation metrics and inference post-processing ---- */
+/* Rank of the ground-truth class in each head's logits row and the per-batch counters the reference's MetricsTracker
+ * accumulates (R/utils/metrics/tracker.py:609-735: per-task top-1 / top-3; R/utils/metrics/chain_accuracy.py:51-364:
+ * chain and partial-chain accuracy; R/utils/metrics/basic.py:79-133: accuracy(topk) is `rank < k`), with no host sync.
+ * logits [B, ld] (`dtype`; head k occupies columns class_off[k] .. class_off[k+1], class_off a HOST array of K+1 ints,
+ * K <= 16); targets int64 [K, B] (class indices; one-hot / soft targets are arg-maxed by the caller as the reference does).
+ * rank[k,i] = #{c : z[c] > z[y] or (z[c] == z[y] and c < y)}  (0 <=> argmax == y; first index wins ties like torch.argmax).
+ * ranks_out int32 [K, B] (nullable).  counters int64 [2K+4] (nullable), ADDED to: [0,K) top-1 correct per task; [K,2K) top-3
+ * correct per task (top-1 when C_k < 3, tracker.py:722-724); [2K] samples with every task right; [2K+1] samples right on
+ * tasks 0..highest task whose target != null_index; [2K+2] samples with any target != null_index; [2K+3] samples. */
+int lnx_hier_metrics(const void* logits, int dtype, int64_t ld, int B, int K, const int* class_off, const int64_t* targets,
+                     int null_index, int* ranks_out, int64_t* counters, lnx_stream_t s);
+/* softmax + top-kk per head for the whole batch (R/inference/handler.py:186-214: softmax -> topk -> .item() per sample and
+ * task).  idx_out int32 [K, B, kk], prob_out float [K, B, kk], ordered by (probability descending, class index ascending);
+ * slots past min(kk, C_k) hold -1 / 0.  kk <= 64. */
+int lnx_hier_topk(const void* logits, int dtype, int64_t ld, int B, int K, const int* class_off, int kk, int* idx_out, float* prob_out,
+                  lnx_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

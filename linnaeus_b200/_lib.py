@@ -46,6 +46,8 @@ SIGNATURES = {
     "lnx_dwconv3_fwd": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "lnx_se_scale": [P, P, P, I, I, I, I, P],
     "lnx_attn_bias_fwd": [P, P, P, I, I, I, I, F, I, P],
+    "lnx_hier_metrics": [P, I, L, I, I, P, P, I, P, P, P],
+    "lnx_hier_topk": [P, I, L, I, I, P, I, P, P, P],
     "lnx_rowscale": [P, P, P, L, I, I, I, P],
     "lnx_rope_table": [P, P, P, I, I, I, I, P],
     "lnx_rope_qk_fwd": [P, P, P, P, P, I, I, I, I, I, F, I, P],
