@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
       tcgen05_fence_after();
       // logits = scale * S (+ bias), handled in the log2 domain.  BIAS: the [32 rows x 16 keys] bias chunk of this warp is
       // staged through shared memory with coalesced 16-byte loads (a lane owns one ROW, so direct loads would touch 32
-      // cache lines per instruction).
+      // cache lines per instruction).  The loads run two chunks ahead of their use (registers), and pass 1 writes the
+      // biased logits back into the S columns of TMEM so pass 2 needs neither the bias nor the scale again.
       const float sl = p.scale * LOG2E;
       float* wb = sBias + sw * (32 * 17);
       const float* bhead = nullptr;
@@ -195,28 +196,42 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
         qt_ = t - j_ * p.n_qt;
         bhead = p.bias + (long long)(((int)blockIdx.x + j_ * (int)gridDim.x) % p.heads) * p.N * p.N;
       }
-      auto stage_bias = [&](int c) {
-        __syncwarp();
+      auto load_bias = [&](int c, float4* dst) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rl = it * 8 + (lane >> 2), c4 = c + (lane & 3) * 4;
           const int gm = min(qt_ * QT + q * 32 + rl, p.N - 1);  // rows past N read row N - 1 (never stored)
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c4 < p.N) bv = __ldg(reinterpret_cast<const float4*>(bhead + (long long)gm * p.N + c4));  // N % 4 == 0
-          float* d = wb + rl * 17 + (lane & 3) * 4;
-          d[0] = bv.x; d[1] = bv.y; d[2] = bv.z; d[3] = bv.w;
+          dst[it] = (c < c_end && c4 < p.N) ? __ldg(reinterpret_cast<const float4*>(bhead + (long long)gm * p.N + c4))  // N % 4 == 0
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto stage_bias = [&](const float4* src) {
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float* d = wb + (it * 8 + (lane >> 2)) * 17 + (lane & 3) * 4;
+          d[0] = src[it].x; d[1] = src[it].y; d[2] = src[it].z; d[3] = src[it].w;
         }
         __syncwarp();
       };
       // pass 1: row max over this half's valid keys
       float mx = -INFINITY;
+      float4 b0[4], b1[4], b2[4];
+      if constexpr (BIAS) {
+        load_bias(c_begin, b0);
+        load_bias(c_begin + 16, b1);
+      }
       for (int c = c_begin; c < c_end; c += 16) {
         float v[16];
+        if constexpr (BIAS) load_bias(c + 32, b2);
         tmem_ld16(trow + c, v);
         if constexpr (BIAS) {
-          stage_bias(c);
+          stage_bias(b0);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], sl, wb[lane * 17 + i] * LOG2E);
+          tmem_st16(trow + c, v);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) b0[it] = b1[it], b1[it] = b2[it];
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= sl;
@@ -230,6 +245,7 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
             if (c + i < p.N) mx = fmaxf(mx, v[i]);
         }
       }
+      if constexpr (BIAS) tmem_st_wait();
       bMax[half * 128 + r] = mx;
       named_bar(1, 256);
       mx = fmaxf(mx, bMax[(half ^ 1) * 128 + r]);
@@ -240,11 +256,9 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_tc2_kernel(const __grid_const
       for (int c = c_begin; c < c_end; c += 16) {
         float v[16];
         tmem_ld16(trow + c, v);
-        if constexpr (BIAS) stage_bias(c);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = fmaf(v[i], sl, -mxl);
-          if constexpr (BIAS) a = fmaf(wb[lane * 17 + i], LOG2E, a);
+          const float a = BIAS ? v[i] - mxl : fmaf(v[i], sl, -mxl);  // BIAS: TMEM already holds the biased log2-domain logit
           float e = ex2f(a);
           if (c + 16 > p.N && c + i >= p.N) e = 0.f;
           sum += e;

@@ -283,9 +283,9 @@ __global__ void __launch_bounds__(128, 5)
                 acc = __ffma2_rn(win[s2][r * STRIDE + dh], wr[dh * 3 + 2], acc);
               }
               acc = __ffma2_rn(acc, sc, sh);
-              if (act == 1) {
-                acc.x = swish_fast(acc.x);
-                acc.y = swish_fast(acc.y);
+              if (act == 1) {  // x * sigmoid(x) with ex2 / rcp (the tanh.approx form costs ~1/8 bf16 ulp more; the kernel is HBM bound)
+                acc.x = __fdividef(acc.x, 1.f + __expf(-acc.x));
+                acc.y = __fdividef(acc.y, 1.f + __expf(-acc.y));
               }
               const __nv_bfloat162 o = __floats2bfloat162_rn(acc.x, acc.y);
               const uint32_t ow = *reinterpret_cast<const uint32_t*>(&o);
