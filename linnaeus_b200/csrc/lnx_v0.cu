@@ -86,6 +86,37 @@ __global__ void im2col3_nchw_kernel(const float* __restrict__ x, T* __restrict__
   }
 }
 
+// RGB image (C = 3, Kpad = 32, bf16 rows of 64 bytes): the 27 taps are gathered into registers (adjacent threads read
+// adjacent pixels of the same image row) and the row leaves as four 16-byte stores instead of 32 two-byte ones
+__global__ void __launch_bounds__(256) im2col3_rgb_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int H, int W, int stride,
+                                                               int Ho, int Wo) {
+  const long long total = (long long)B * Ho * Wo;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(r % Wo);
+    const int ho = (int)((r / Wo) % Ho);
+    const long long b = r / ((long long)Wo * Ho);
+    const float* img = x + b * 3 * (long long)H * W;
+    float v[32];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int h = ho * stride - 1 + tap / 3, w = wo * stride - 1 + tap % 3;
+      const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[tap * 3 + c] = ok ? __ldg(img + ((long long)c * H + h) * W + w) : 0.f;
+    }
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0.f;
+    uint4* dst = reinterpret_cast<uint4*>(out + r * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Vec16<bf16> o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o.set(e, v[q * 8 + e]);
+      st16(reinterpret_cast<bf16*>(dst + q), o);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- maxpool 3x3 s2 p1
 template <typename T>
 __global__ void maxpool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
@@ -413,6 +444,8 @@ extern "C" int lnx_im2col3x3(const void* x, int x_is_nchw_f32, void* out, int B,
   if (x_is_nchw_f32) {
     const long long total = (long long)B * Ho * Wo;
     if (dtype == LNX_F32) im2col3_nchw_kernel<float><<<grid_for(total, 128), 128, 0, st>>>((const float*)x, (float*)out, B, H, W, C, stride, Ho, Wo, Kpad);
+    else if (dtype == LNX_BF16 && C == 3 && Kpad == 32 && lnx_aligned16(out))
+      im2col3_rgb_bf16_kernel<<<grid_for(total, 256), 256, 0, st>>>((const float*)x, (bf16*)out, B, H, W, stride, Ho, Wo);
     else if (dtype == LNX_BF16) im2col3_nchw_kernel<bf16><<<grid_for(total, 128), 128, 0, st>>>((const float*)x, (bf16*)out, B, H, W, C, stride, Ho, Wo, Kpad);
     else return LNX_ERR_DTYPE;
   } else {

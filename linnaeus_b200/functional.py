@@ -113,7 +113,7 @@ class _Linear(torch.autograd.Function):
     """y = act(x W^T + b) (+ residual).  nn.Linear (+GELU/ReLU) of the reference."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, weight_c, act, residual, x_ld, out_dtype, row_scale, rpg):
+    def forward(ctx, x, weight, bias, weight_c, act, residual, x_ld, out_dtype, row_scale, rpg, grad_on=True):
         K = weight.shape[1]
         N = weight.shape[0]
         lead = x.shape[:-1]
@@ -131,7 +131,8 @@ class _Linear(torch.autograd.Function):
             wc_use = _c(weight.detach())
         else:
             wc_use = wc
-        need_grad = any(ctx.needs_input_grad)
+        # ctx.needs_input_grad ignores torch.no_grad(): the wrapper passes the grad mode so inference saves nothing
+        need_grad = grad_on and any(ctx.needs_input_grad)
         aux = torch.empty((M, N), dtype=out_dtype, device=x2.device) if (act != ACT_NONE and need_grad) else None
         res2 = _c(residual).view(M, N) if residual is not None else None
         y = gemm(x2, wc_use, M, N, K, lda=lda, out_dtype=out_dtype, bias=bias, act=act, aux_out=aux, residual=res2,
@@ -188,11 +189,11 @@ class _Linear(torch.autograd.Function):
                 _grad_done(bias)
             else:
                 db = db_buf
-        return dx, dw, db, None, None, d_res, None, None, None, None
+        return dx, dw, db, None, None, d_res, None, None, None, None, None
 
 
 def linear(x, weight, bias=None, weight_c=None, act=None, residual=None, x_ld=None, out_dtype=None, row_scale=None, rows_per_group=0):
-    return _Linear.apply(x, weight, bias, weight_c, _ACT[act], residual, x_ld, out_dtype, row_scale, rows_per_group)
+    return _Linear.apply(x, weight, bias, weight_c, _ACT[act], residual, x_ld, out_dtype, row_scale, rows_per_group, torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------- two-layer MLP
@@ -205,7 +206,7 @@ class _Mlp2(torch.autograd.Function):
     dgamma = rowsum(dW2_raw * W2) + b2 * db2_raw  (no extra pass over activations)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, w1c, w2c, act, residual, col_scale, row_scale, rpg):
+    def forward(ctx, x, w1, b1, w2, b2, w1c, w2c, act, residual, col_scale, row_scale, rpg, grad_on=True):
         K = w1.shape[1]
         Hd = w1.shape[0]
         N = w2.shape[0]
@@ -214,7 +215,7 @@ class _Mlp2(torch.autograd.Function):
         M = x2.shape[0]
         w1c = w1c if w1c is not None else compute_copy(w1, x2.dtype)
         w2c = w2c if w2c is not None else compute_copy(w2, x2.dtype)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = grad_on and any(ctx.needs_input_grad)  # grad_on: see _Linear.forward
         # GELU: the forward epilogue stores gelu'(pre) (one tanh serves both), so the backward epilogue is a multiply
         pre = torch.empty((M, Hd), dtype=x2.dtype, device=x2.device) if need_grad else None
         save_dg = need_grad and act == ACT_GELU
@@ -279,11 +280,11 @@ class _Mlp2(torch.autograd.Function):
         for prm, snk in ((p_w1, s_w1), (p_b1, s_b1), (p_w2, s_w2), (p_b2, s_b2)):
             if snk is not None:
                 _grad_done(prm)
-        return dx, dw1, db1, dw2, db2, None, None, None, d_res, d_cs, None, None
+        return dx, dw1, db1, dw2, db2, None, None, None, d_res, d_cs, None, None, None
 
 
 def mlp2(x, w1, b1, w2, b2, w1c=None, w2c=None, act="gelu", residual=None, col_scale=None, row_scale=None, rows_per_group=0):
-    return _Mlp2.apply(x, w1, b1, w2, b2, w1c, w2c, _ACT[act], residual, col_scale, row_scale, rows_per_group)
+    return _Mlp2.apply(x, w1, b1, w2, b2, w1c, w2c, _ACT[act], residual, col_scale, row_scale, rows_per_group, torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------- LayerNorm
