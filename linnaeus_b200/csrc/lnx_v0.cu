@@ -431,6 +431,145 @@ __global__ void __launch_bounds__(64) attn_bias_fwd_kernel(const T* __restrict__
   }
 }
 
+// short sequences (N <= 64: the last stage, 49 patches + extras) at any head_dim that is a multiple of 32: one CTA per
+// (batch, head) keeps K and V in shared memory as fp32 (K rows padded by 4 floats: conflict-free 16-byte reads with a lane
+// per key), a warp per query row: lanes = keys for q k^T + bias and the softmax (two keys per lane), lanes = head dims for
+// P V.  The generic kernel above holds a whole q and o row per thread (2 x head_dim registers) and runs at one warp per SM
+// sub-partition for these shapes.
+template <typename T>
+__global__ void __launch_bounds__(128) attn_small_kernel(const T* __restrict__ qkv, const float* __restrict__ bias, T* __restrict__ out, int heads,
+                                                         int N, int hd, float scale) {
+  extern __shared__ __align__(16) float sm_attn[];
+  constexpr int V = Vec16<T>::N;
+  const int ks = hd + 4;
+  float* Ks = sm_attn;
+  float* Vs = Ks + N * ks;
+  float* sq = Vs + N * hd;
+  float* sp = sq + 16 * hd;  // [4 warps][4 rows][hd] q rows, then [4][4][64] probabilities
+  const int bh = blockIdx.x;
+  const int b = bh / heads, h = bh - b * heads;
+  const long long row_stride = 3LL * heads * hd;
+  const T* base = qkv + (long long)b * N * row_stride + (long long)h * hd;
+  const int vec_per_row = hd / V;
+  for (int t = threadIdx.x; t < N * vec_per_row; t += blockDim.x) {
+    const int j = t / vec_per_row, dv = (t - j * vec_per_row) * V;
+    const T* tok = base + (long long)j * row_stride + dv;
+    const Vec16<T> kv = ld16(tok + (long long)heads * hd), vv = ld16(tok + 2LL * heads * hd);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      Ks[j * ks + dv + e] = kv.get(e);
+      Vs[j * hd + dv + e] = vv.get(e);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int R = 4;  // query rows per warp pass: every K / V value read from shared memory feeds R rows
+  float* q = sq + warp * R * hd;
+  float* pw = sp + warp * R * 64;
+  const int j0 = lane, j1 = lane + 32;
+  const float* k0 = Ks + min(j0, N - 1) * ks;
+  const float* k1 = Ks + min(j1, N - 1) * ks;
+  // the q rows and bias values of the NEXT pass are fetched while this one is computed (global latency per pass otherwise)
+  float qn[R][4], bn0[R], bn1[R];
+  auto fetch = [&](int i0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + r;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) qn[r][t] = (i < N && lane + 32 * t < hd) ? to_f32(base[(long long)i * row_stride + lane + 32 * t]) * scale : 0.f;
+      bn0[r] = bn1[r] = 0.f;
+      if (bias && i < N) {
+        const float* brow = bias + ((long long)h * N + i) * N;
+        if (j0 < N) bn0[r] = brow[j0];
+        if (j1 < N) bn1[r] = brow[j1];
+      }
+    }
+  };
+  fetch(warp * R);
+  for (int i0 = warp * R; i0 < N; i0 += 4 * R) {
+    float bc0[R], bc1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < hd) q[r * hd + lane + 32 * t] = qn[r][t];
+      bc0[r] = bn0[r];
+      bc1[r] = bn1[r];
+    }
+    __syncwarp();
+    fetch(i0 + 4 * R);
+    float s0[R], s1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) s0[r] = s1[r] = 0.f;
+#pragma unroll 2
+    for (int d = 0; d < hd; d += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(k0 + d);
+      const float4 c = *reinterpret_cast<const float4*>(k1 + d);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 qv = *reinterpret_cast<const float4*>(q + r * hd + d);
+        s0[r] = fmaf(qv.x, a.x, s0[r]); s0[r] = fmaf(qv.y, a.y, s0[r]); s0[r] = fmaf(qv.z, a.z, s0[r]); s0[r] = fmaf(qv.w, a.w, s0[r]);
+        s1[r] = fmaf(qv.x, c.x, s1[r]); s1[r] = fmaf(qv.y, c.y, s1[r]); s1[r] = fmaf(qv.z, c.z, s1[r]); s1[r] = fmaf(qv.w, c.w, s1[r]);
+      }
+    }
+    float inv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float x0 = j0 < N ? s0[r] + bc0[r] : -INFINITY, x1 = j1 < N ? s1[r] + bc1[r] : -INFINITY;
+      const float m = warp_max(fmaxf(x0, x1));
+      const float e0 = j0 < N ? (sizeof(T) == 4 ? expf(x0 - m) : __expf(x0 - m)) : 0.f;
+      const float e1 = j1 < N ? (sizeof(T) == 4 ? expf(x1 - m) : __expf(x1 - m)) : 0.f;
+      inv[r] = 1.f / warp_sum(e0 + e1);
+      pw[r * 64 + j0] = e0;
+      pw[r * 64 + j1] = e1;
+    }
+    __syncwarp();
+    float o[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) o[r][t] = 0.f;
+    for (int j = 0; j < N; ++j) {
+      float vv[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) vv[t] = lane + 32 * t < hd ? Vs[j * hd + lane + 32 * t] : 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float pj = pw[r * 64 + j];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o[r][t] = fmaf(pj, vv[t], o[r][t]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + r;
+      if (i < N) {
+        T* dst = out + ((long long)b * N + i) * heads * hd + (long long)h * hd;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (lane + 32 * t < hd) dst[lane + 32 * t] = from_f32<T>(o[r][t] * inv[r]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T>
+int launch_attn_small(const void* qkv, const float* bias, void* out, int B, int heads, int N, int hd, float scale, cudaStream_t st) {
+  const size_t smem = ((size_t)N * (hd + 4) + (size_t)N * hd + 16 * hd + 16 * 64) * sizeof(float);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    if (cudaFuncSetAttribute(attn_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return LNX_ERR_UNSUPPORTED;
+    }
+    smem_set = smem;
+  }
+  attn_small_kernel<T><<<B * heads, 128, smem, st>>>((const T*)qkv, bias, (T*)out, heads, N, hd, scale);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
 inline int grid_for(long long total, int threads) { return (int)max(1LL, min((long long)kNumSMs * 16, (total + threads - 1) / threads)); }
 
 }  // namespace
@@ -557,8 +696,13 @@ extern "C" int lnx_attn_bias_fwd(const void* qkv, const float* bias, void* out, 
     if (r != LNX_ERR_UNSUPPORTED) return r;
     if (getenv("LNX_ATTN_NO_FALLBACK") && hd <= 64 && N <= 240) return LNX_ERR_UNSUPPORTED;
   }
-  dim3 grid((N + 63) / 64, B * heads);
   cudaStream_t st = (cudaStream_t)s;
+  if (N <= 64 && hd % 32 == 0 && hd <= 128 && lnx_aligned16(qkv)) {  // K / V resident in shared memory, a warp per query row
+    const int r = dtype == LNX_F32 ? launch_attn_small<float>(qkv, bias, out, B, heads, N, hd, scale, st)
+                                   : launch_attn_small<bf16>(qkv, bias, out, B, heads, N, hd, scale, st);
+    if (r != LNX_ERR_UNSUPPORTED) return r;
+  }
+  dim3 grid((N + 63) / 64, B * heads);
 #define LNX_AB(HDIM)                                                                                                                   \
   case HDIM:                                                                                                                           \
     if (dtype == LNX_F32) attn_bias_fwd_kernel<float, HDIM><<<grid, 64, 0, st>>>((const float*)qkv, bias, (float*)out, heads, N, scale); \

@@ -101,7 +101,8 @@ def test_v0_kernels_against_torch():
     z = torch.empty_like(x)
     call("lnx_se_scale", x.data_ptr(), gate.data_ptr(), z.data_ptr(), B, H * W, C, 0)
     assert float((z - x * torch.sigmoid(gate)[:, None, None, :]).abs().max()) < 1e-5
-    for hd, heads, N in ((48, 8, 53), (96, 8, 200), (64, 2, 17), (48, 8, 200), (32, 4, 132), (16, 2, 240)):
+    # (96, 8, 53), (128, 3, 64), (32, 5, 1), (64, 2, 17): the short-sequence shared-memory kernel (fp32; bf16 when head_dim > 64)
+    for hd, heads, N in ((48, 8, 53), (96, 8, 200), (64, 2, 17), (48, 8, 200), (32, 4, 132), (16, 2, 240), (96, 8, 53), (128, 3, 64), (32, 5, 1)):
         qkv = torch.randn(B, N, 3, heads, hd, device=DEV)
         bias = torch.randn(heads, N, N, device=DEV)
         o = torch.empty(B, N, heads * hd, device=DEV)
