@@ -237,6 +237,20 @@ int lnx_hier_metrics(const void* logits, int dtype, int64_t ld, int B, int K, co
 int lnx_hier_topk(const void* logits, int dtype, int64_t ld, int B, int K, const int* class_off, int kk, int* idx_out, float* prob_out,
                   lnx_stream_t s);
 
+/* ---- batch augmentation feeding the model: the apply step of selective mixup ---- */
+/* out[i, :] = lam * x[i, :] + (1 - lam) * x[perm[i], :]  (fp32 mul, mul, add: bit-equal to the reference expression
+ * `lam * v + (1 - lam) * v[perm]`, R/aug/gpu/selective_mixup.py:150,177).  x, out float [B, row] (out != x); perm int64 [B];
+ * lam a DEVICE scalar (the Beta sample never visits the host). */
+int lnx_mix_pairs(const float* x, const int64_t* perm, const float* lam, float* out, int B, int64_t row, lnx_stream_t s);
+/* Metadata side of selective mixup (R/aug/gpu/selective_mixup.py:320-328,371-392,394-560).  aux float [B, D] and mask
+ * uint8 (torch.bool) [B, D] are first "all-or-nothing" enforced IN PLACE: a chunk [lo, hi) with any entry == 0 is zeroed
+ * and its mask cleared.  Then per sample i and chunk: both the original and the partner (perm[i]) chunk non-zero -> the
+ * original iff pick[i] < 0.5 else the partner; exactly one non-zero -> that one; both zero -> zeros / mask 0; written to
+ * out_aux / out_mask (distinct buffers; entries outside every chunk are not written).  chunk_bounds: HOST array of
+ * 2 * n_chunks ints (lo, hi), n_chunks <= 16; pick float [B] uniform numbers (device). */
+int lnx_mix_meta_chunks(float* aux, uint8_t* mask, const int64_t* perm, const float* pick, const int* chunk_bounds, int n_chunks,
+                        float* out_aux, uint8_t* out_mask, int B, int D, lnx_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,138 @@
+"""GPU: selective mixup (lnx_mix_pairs / lnx_mix_meta_chunks through linnaeus_b200.aug) against the CPU oracle and the committed
+outputs of the unmodified reference class (tests/golden/aug_*.npz).  Bit-exact: the blend is the reference's fp32 expression."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import aug_oracle as AO
+from tests.support.golden_aug import CASES, covered_columns, load_golden, make_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _A():
+    import linnaeus_b200.aug as A
+
+    return A
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_mixup_apply_matches_reference_golden(name):
+    A = _A()
+    c, g = make_case(name), load_golden(name)
+    images, targets = _t(c["images"]), {k: _t(v) for k, v in c["targets"].items()}
+    aux, masks, gids = _t(c["aux"]), _t(c["masks"]), _t(c["group_ids"])
+    eff = A.exclude_null_samples_from_mixup((images, targets, aux, masks, gids))[4]
+    assert np.array_equal(eff.cpu().numpy(), g["eff_gids"])
+    mi, mt, ma, mm = A.mixup_apply(images, targets, aux, masks, _t(g["perm"]), _t(g["lam"]), _t(g["pick"]), c["chunks"])
+    assert np.array_equal(mi.cpu().numpy(), g["mixed_images"])
+    for k in targets:
+        assert np.array_equal(mt[k].cpu().numpy(), g["mixed_targets." + k])
+    cov = covered_columns(c["chunks"], c["aux"].shape[1])
+    assert np.array_equal(ma.cpu().numpy()[:, cov], g["mixed_aux"][:, cov])
+    assert np.array_equal(mm.cpu().numpy()[:, cov], g["mixed_masks"][:, cov])
+    assert np.array_equal(aux.cpu().numpy(), g["aux_after"]) and np.array_equal(masks.cpu().numpy(), g["masks_after"])
+
+
+@pytest.mark.parametrize("B,S,D,chunks", [(1, 4, 3, None), (256, 32, 15, [(0, 2), (2, 5), (5, 15)]), (37, 7, 6, [(1, 3), (3, 3), (4, 6)])])
+def test_mixup_apply_bit_exact_vs_oracle(B, S, D, chunks):
+    """Odd row lengths (scalar path), empty chunks, uncovered columns, one-sample batches, full-size batches."""
+    A = _A()
+    rng = np.random.default_rng(B + S)
+    images = rng.standard_normal((B, 3, S, S)).astype(np.float32)
+    targets = {"taxa_L10": rng.random((B, 11)).astype(np.float32), "taxa_L20": rng.random((B, 4)).astype(np.float32)}
+    aux = rng.standard_normal((B, D)).astype(np.float32)
+    aux[rng.random((B, D)) < 0.2] = 0.0
+    masks = rng.random((B, D)) < 0.8
+    perm = rng.permutation(B)
+    lam, pick = np.float32(rng.random()), rng.random(B).astype(np.float32)
+    a_dev, m_dev = _t(aux), _t(masks)
+    mi, mt, ma, mm = A.mixup_apply(_t(images), {k: _t(v) for k, v in targets.items()}, a_dev, m_dev, _t(perm), torch.tensor(lam, device=DEV),
+                                   _t(pick), chunks)
+    a_ref, m_ref = aux.copy(), masks.copy()
+    oi, ot, oa, om = AO.mixup_apply(images, targets, a_ref, m_ref, perm, lam, pick, chunks)
+    assert np.array_equal(mi.cpu().numpy(), oi)
+    for k in targets:
+        assert np.array_equal(mt[k].cpu().numpy(), ot[k])
+    assert np.array_equal(ma.cpu().numpy(), oa) and np.array_equal(mm.cpu().numpy(), om)  # uncovered columns: zeros on both sides
+    assert np.array_equal(a_dev.cpu().numpy(), a_ref) and np.array_equal(m_dev.cpu().numpy(), m_ref)
+
+
+def test_device_rng_mode_is_a_valid_selective_mixup():
+    """rng='device' (no host sync): the permutation stays inside groups, fixes excluded samples, and the outputs equal the oracle's
+    apply step for the draws it made; PROB = 0 returns the batch untouched (including the metadata it was given)."""
+    A = _A()
+    c = make_case("aug_three_chunks")
+    torch.manual_seed(5)
+    mk = lambda: (_t(c["images"]), {k: _t(v) for k, v in c["targets"].items()}, _t(c["aux"]), _t(c["masks"]), _t(c["group_ids"]))
+    mix = A.GPUSelectiveMixup({"PROB": 1.0, "ALPHA": 0.4, "meta_chunk_bounds_list": list(c["chunks"])})
+    seen_moves = 0
+    for _ in range(4):
+        batch = mk()
+        mi, mt, ma, mm = mix(batch)
+        eff = AO.exclude_null_group_ids(c["targets"], c["group_ids"])
+        perm = mix.last_permutation.cpu().numpy()
+        assert AO.is_ingroup_permutation(perm, eff)
+        seen_moves += int((perm != np.arange(len(perm))).sum())
+        # lam is recoverable from any moved pixel; check the blend through the oracle with lam solved from the output
+        moved = np.nonzero(perm != np.arange(len(perm)))[0]
+        if len(moved):
+            i = moved[0]
+            x, xp, o = c["images"][i].ravel(), c["images"][perm[i]].ravel(), mi[i].cpu().numpy().ravel()
+            j = np.argmax(np.abs(x - xp))
+            lam = (o[j] - xp[j]) / (x[j] - xp[j])
+            assert 0.0 <= lam <= 1.0
+            np.testing.assert_allclose(o, lam * x + (1 - lam) * xp, rtol=1e-4, atol=1e-5)
+        # metadata chunks are copied whole from the sample itself or its partner
+        a_enf, m_enf = c["aux"].copy(), c["masks"].copy()
+        AO.enforce_all_or_nothing(a_enf, m_enf, c["chunks"])
+        got = ma.cpu().numpy()
+        for i in range(len(perm)):
+            for lo, hi in c["chunks"]:
+                ok = [np.array_equal(got[i, lo:hi], a_enf[s, lo:hi]) for s in (i, perm[i])] + [not got[i, lo:hi].any()]
+                assert any(ok)
+    assert seen_moves > 0
+    off = A.GPUSelectiveMixup({"PROB": 0.0, "ALPHA": 0.4, "meta_chunk_bounds_list": list(c["chunks"])})
+    batch = mk()
+    mi, mt, ma, mm = off(batch)
+    assert torch.equal(mi, batch[0]) and all(torch.equal(mt[k], batch[1][k]) for k in mt)
+    assert np.array_equal(ma.cpu().numpy(), c["aux"]) and np.array_equal(mm.cpu().numpy(), c["masks"])
+    assert np.array_equal(batch[2].cpu().numpy(), c["aux"]) and np.array_equal(batch[3].cpu().numpy(), c["masks"])
+
+
+def test_reference_rng_mode_replays_the_reference_draw_sequence():
+    """rng='reference' makes the reference's RNG calls in the reference's order: with the same device seed its draws are the ones
+    obtained by replaying that sequence by hand."""
+    A = _A()
+    c = make_case("aug_three_chunks")
+    batch = (_t(c["images"]), {k: _t(v) for k, v in c["targets"].items()}, _t(c["aux"]), _t(c["masks"]), _t(c["group_ids"]))
+    eff = A.exclude_null_samples_from_mixup(batch)[4]
+    mix = A.GPUSelectiveMixup({"PROB": 1.0, "ALPHA": 0.4, "meta_chunk_bounds_list": list(c["chunks"])}, rng="reference")
+    torch.manual_seed(123)
+    mi, mt, ma, mm = mix(batch)
+    torch.manual_seed(123)
+    torch.rand(1, device=DEV)
+    perm = torch.arange(len(eff), device=DEV)
+    for gid in eff.unique():
+        if gid.item() == -1:
+            continue
+        idx = (eff == gid).nonzero(as_tuple=True)[0]
+        if idx.numel() > 1:
+            perm[idx] = idx[torch.randperm(idx.numel(), device=DEV)]
+    lam = torch.distributions.beta.Beta(0.4, 0.4).sample()
+    pick = torch.rand(len(eff), device=DEV)
+    assert torch.equal(perm, mix.last_permutation)
+    a2, m2 = c["aux"].copy(), c["masks"].copy()
+    oi, ot, oa, om = AO.mixup_apply(c["images"], c["targets"], a2, m2, perm.cpu().numpy(), lam.numpy(), pick.cpu().numpy(), c["chunks"])
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(ma.cpu().numpy(), oa) and np.array_equal(mm.cpu().numpy(), om)
+
+
+def test_aug_rejects_cpu_tensors():
+    A = _A()
+    with pytest.raises(RuntimeError):
+        A.mixup_apply(torch.zeros(2, 3), {}, torch.zeros(2, 2), torch.zeros(2, 2, dtype=torch.bool), torch.arange(2), torch.tensor(0.5), torch.zeros(2), None)
