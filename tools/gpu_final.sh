@@ -9,3 +9,8 @@ timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 timeout 300 python bench.py --mode infer --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_infer_b256.log 2>&1; echo "infer rc $?"; tail -1 gpurun_out/bench_infer_b256.log | cut -c1-400
 timeout 300 python bench.py --mode infer --arch v0 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v0_infer_b256.log 2>&1; echo "v0 infer rc $?"; tail -1 gpurun_out/bench_v0_infer_b256.log | cut -c1-400
 timeout 300 python tools/prof_metrics.py > gpurun_out/prof_metrics.log 2>&1; echo "metrics rc $?"; cat gpurun_out/prof_metrics.log
+timeout 300 python bench.py --variant md --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_md_b256.log 2>&1; echo "md rc $?"; tail -1 gpurun_out/bench_md_b256.log | cut -c1-200
+timeout 400 python bench.py --variant xl --img 384 --batch 32 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_xl_b32.log 2>&1; echo "xl rc $?"; tail -1 gpurun_out/bench_xl_b32.log | cut -c1-200
+timeout 300 python bench.py --mode infer --arch v0 --batch 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_v0_infer_b1.log 2>&1; echo "v0 b1 rc $?"; tail -1 gpurun_out/bench_v0_infer_b1.log | cut -c1-200
+timeout 300 python bench.py --mode infer --arch v0 --batch 1024 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v0_infer_b1024.log 2>&1; echo "v0 b1024 rc $?"; tail -1 gpurun_out/bench_v0_infer_b1024.log | cut -c1-200
+timeout 300 python tools/prof_aug.py > gpurun_out/prof_aug.log 2>&1; echo "aug rc $?"; cat gpurun_out/prof_aug.log
