@@ -250,6 +250,16 @@ int lnx_mix_pairs(const float* x, const int64_t* perm, const float* lam, float* 
  * 2 * n_chunks ints (lo, hi), n_chunks <= 16; pick float [B] uniform numbers (device). */
 int lnx_mix_meta_chunks(float* aux, uint8_t* mask, const int64_t* perm, const float* pick, const int* chunk_bounds, int n_chunks,
                         float* out_aux, uint8_t* out_mask, int B, int D, lnx_stream_t s);
+/* Selective CutMix, image side (R/aug/gpu/selective_cutmix.py:204-236): out = x, except that inside the box
+ * [h1, h2) x [w1, w2) of dims 2 / 3 every sample with group_ids[i] != -1 takes the pixels of x[perm[i]].  x, out float
+ * [B, C, H, W] (out != x); perm, group_ids int64 [B]. */
+int lnx_cutmix_paste(const float* x, const int64_t* perm, const int64_t* group_ids, float* out, int B, int C, int H, int W, int h1, int w1,
+                     int h2, int w2, lnx_stream_t s);
+/* Selective CutMix, target side (selective_cutmix.py:266-269): out[i] = group_ids[i] != -1 ?
+ * coef_self * x[i] + coef_partner * x[perm[i]] : x[i]   (fp32 mul, mul, add; the caller passes (float)lam_adjusted and
+ * (float)(1.0 - lam_adjusted), the two Python-float scalars of the reference expression). */
+int lnx_mix_pairs_valid(const float* x, const int64_t* perm, const int64_t* group_ids, float coef_self, float coef_partner, float* out, int B,
+                        int64_t row, lnx_stream_t s);
 
 #ifdef __cplusplus
 }

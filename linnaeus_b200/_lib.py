@@ -50,6 +50,8 @@ SIGNATURES = {
     "lnx_hier_topk": [P, I, L, I, I, P, I, P, P, P],
     "lnx_mix_pairs": [P, P, P, P, I, L, P],
     "lnx_mix_meta_chunks": [P, P, P, P, P, I, P, P, I, I, P],
+    "lnx_cutmix_paste": [P, P, P, P, I, I, I, I, I, I, I, I, P],
+    "lnx_mix_pairs_valid": [P, P, P, F, F, P, I, L, P],
     "lnx_rowscale": [P, P, P, L, I, I, I, P],
     "lnx_rope_table": [P, P, P, I, I, I, I, P],
     "lnx_rope_qk_fwd": [P, P, P, P, P, I, I, I, I, I, F, I, P],

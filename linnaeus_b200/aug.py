@@ -164,3 +164,104 @@ class GPUSelectiveMixup:
         aux_info.copy_(torch.where(skip, aux0, aux_info))
         meta_masks.copy_(torch.where(skip, mask0, meta_masks))
         return mi, mt, torch.where(skip, aux0, ma), torch.where(skip, mask0, mm)
+
+
+# ----------------------------------------------------------------------------- selective CutMix
+def rand_bbox(size, lam: float):
+    """R/aug/utils.py:16-43 (Python ``random`` for the centre; note its W = size[2], H = size[3] naming)."""
+    import math
+    import random
+
+    W, H = size[2], size[3]
+    cut_rat = math.sqrt(1.0 - lam)
+    cut_w, cut_h = int(W * cut_rat), int(H * cut_rat)
+    cx, cy = random.randint(0, W), random.randint(0, H)
+    return max(0, cx - cut_w // 2), max(0, cy - cut_h // 2), min(W, cx + cut_w // 2), min(H, cy + cut_h // 2)
+
+
+def cutmix_apply(images, targets: dict, aux_info, meta_masks, group_ids, perm, box, pick, chunk_bounds):
+    """The apply step of selective CutMix for given draws (R/aug/gpu/selective_cutmix.py:204-437).  ``box`` = (bbx1, bby1, bbx2,
+    bby2) HOST ints indexing dims 2 / 3 of ``images`` as the reference does; grouped samples (group id != -1) take their
+    partner's pixels inside it and blend soft targets with lam_adjusted = 1 - box_area / (H * W); metadata as in mixup."""
+    _require_cuda(images)
+    B, C, H, W = images.shape
+    dev = images.device
+    perm = perm.to(device=dev, dtype=torch.int64).contiguous()
+    gids = group_ids.to(device=dev, dtype=torch.int64).contiguous()
+    pick = pick.to(device=dev, dtype=torch.float32).contiguous()
+    bbx1, bby1, bbx2, bby2 = (int(v) for v in box)
+    lam_adjusted = 1.0 - ((bbx2 - bbx1) * (bby2 - bby1)) / (H * W)
+    if images.dtype != torch.float32:
+        raise TypeError(f"cutmix_apply works on float32 images, got {images.dtype}")
+    xc = images.contiguous()
+    mixed_images = torch.empty_like(xc)
+    call("lnx_cutmix_paste", xc.data_ptr(), perm.data_ptr(), gids.data_ptr(), mixed_images.data_ptr(), B, C, H, W, bbx1, bby1, bbx2, bby2)
+    mixed_targets = {}
+    for k, v in targets.items():
+        if v.dtype != torch.float32:
+            raise TypeError(f"cutmix_apply blends float32 targets, got {v.dtype} for {k}")
+        vc = v.contiguous()
+        out = torch.empty_like(vc)
+        call("lnx_mix_pairs_valid", vc.data_ptr(), perm.data_ptr(), gids.data_ptr(), float(lam_adjusted), float(1 - lam_adjusted), out.data_ptr(), B,
+             vc.numel() // B)
+        mixed_targets[k] = out
+    if aux_info.ndim < 2 or aux_info.shape[1] == 0:
+        return mixed_images, mixed_targets, torch.empty_like(aux_info), torch.empty_like(meta_masks)
+    D = aux_info.shape[1]
+    bounds = list(chunk_bounds) if chunk_bounds is not None else [(0, D)]
+    if not (aux_info.is_contiguous() and meta_masks.is_contiguous() and aux_info.dtype == torch.float32 and meta_masks.dtype == torch.bool):
+        raise TypeError("aux_info must be contiguous float32 and meta_masks contiguous bool (they are enforced in place)")
+    out_aux, out_mask = torch.zeros_like(aux_info), torch.zeros_like(meta_masks)
+    if bounds:
+        flat = (ctypes.c_int * (2 * len(bounds)))(*[int(v) for b in bounds for v in b])
+        call("lnx_mix_meta_chunks", aux_info.data_ptr(), meta_masks.data_ptr(), perm.data_ptr(), pick.data_ptr(), flat, len(bounds),
+             out_aux.data_ptr(), out_mask.data_ptr(), B, D)
+    return mixed_images, mixed_targets, out_aux, out_mask
+
+
+class GPUSelectiveCutMix(GPUSelectiveMixup):
+    """Group-aware CutMix (R/aug/gpu/selective_cutmix.py:14-543): ``PROB`` (default 1.0), ``ALPHA`` (default 1.0), optional
+    ``MINMAX`` bounds on lambda, ``meta_chunk_bounds_list``.  lambda is sampled on the host (as the reference's Beta sample is)
+    and the box is drawn with Python ``random`` like ``rand_bbox``; ``rng="device"`` additionally takes the probability gate
+    from the CPU generator and builds the permutation with two sorts, so nothing waits for the device."""
+
+    def __init__(self, mix_config: dict[str, Any], config=None, rng: str = "device"):
+        super().__init__(mix_config, config, rng)
+        self.minmax = mix_config.get("MINMAX", None)
+        self.last_box = None
+
+    def __call__(self, batch, exclude_null_samples: bool = True, null_task_keys=None):
+        if exclude_null_samples:
+            batch = exclude_null_samples_from_mixup(batch, null_task_keys, config=self.config)
+        images, targets, aux_info, meta_masks, group_ids = batch
+        _require_cuda(images)
+        dev = images.device
+        B, C, H, W = images.shape
+        prob = self.mix_config.get("PROB", 1.0)
+        alpha = float(self.mix_config.get("ALPHA", 1.0))
+        if self.rng == "reference":
+            if torch.rand(1, device=dev).item() > prob:
+                return images, targets, aux_info, meta_masks
+            if (group_ids == -1).all():
+                return images, targets, aux_info, meta_masks
+            perm = self._reference_permutation(group_ids)
+        else:
+            if torch.rand(1).item() > prob:  # CPU generator: a host-side decision, no device sync
+                return images, targets, aux_info, meta_masks
+            perm = ingroup_permutation(group_ids)
+        lam = torch.distributions.beta.Beta(alpha, alpha).sample()  # host tensor, as in the reference
+        if self.minmax is not None:
+            lam = self.minmax[0] + (self.minmax[1] - self.minmax[0]) * lam
+        box = rand_bbox((1, C, H, W), lam.item())
+        self.last_permutation, self.last_box = perm, box
+        pick = torch.rand(B, device=dev)
+        if self.rng == "reference":
+            return cutmix_apply(images, targets, aux_info, meta_masks, group_ids, perm, box, pick, self.chunk_bounds)
+        # "no group at all" cannot be tested without a sync: the image / target kernels are exact no-ops for ungrouped samples,
+        # and the metadata (including its in-place enforcement) is restored on the device
+        skip = (group_ids == -1).all().reshape(1)
+        aux0, mask0 = aux_info.clone(), meta_masks.clone()
+        mi, mt, ma, mm = cutmix_apply(images, targets, aux_info, meta_masks, group_ids, perm, box, pick, self.chunk_bounds)
+        aux_info.copy_(torch.where(skip, aux0, aux_info))
+        meta_masks.copy_(torch.where(skip, mask0, meta_masks))
+        return mi, mt, torch.where(skip, aux0, ma), torch.where(skip, mask0, mm)

@@ -90,7 +90,79 @@ __global__ void meta_pick_kernel(const float* __restrict__ aux, const unsigned c
   }
 }
 
+// selective CutMix (R/aug/gpu/selective_cutmix.py:204-273): one box for the whole batch; inside it a grouped sample
+// (group id != -1) takes its partner's pixels.  grid (chunks of an image, samples); e runs over C*H*W (float4 when W % 4 == 0)
+template <int V>
+__global__ void __launch_bounds__(256) cutmix_paste_kernel(const float* __restrict__ x, const long long* __restrict__ perm,
+                                                           const long long* __restrict__ gids, float* __restrict__ out, long long img_v, int H, int W,
+                                                           int h1, int w1, int h2, int w2) {
+  const long long i = blockIdx.y;
+  const long long j = gids[i] != -1 ? perm[i] : i;
+  const float* a = x + i * img_v * V;
+  const float* b = x + j * img_v * V;
+  float* o = out + i * img_v * V;
+  const int wv = W / V;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < img_v; e += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(e % wv) * V;
+    const int h = (int)((e / wv) % H);
+    const bool row_in = j != i && h >= h1 && h < h2;
+    if (V == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(a) + e);
+      if (row_in && w + 3 >= w1 && w < w2) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(b) + e);
+        if (w >= w1 && w < w2) v.x = p.x;
+        if (w + 1 >= w1 && w + 1 < w2) v.y = p.y;
+        if (w + 2 >= w1 && w + 2 < w2) v.z = p.z;
+        if (w + 3 >= w1 && w + 3 < w2) v.w = p.w;
+      }
+      reinterpret_cast<float4*>(o)[e] = v;
+    } else {
+      o[e] = (row_in && w >= w1 && w < w2) ? __ldg(b + e) : __ldg(a + e);
+    }
+  }
+}
+
+// out[i] = group id != -1 ? ca * x[i] + cb * x[perm[i]] : x[i]   (soft targets under CutMix; coefficients by value)
+__global__ void mix_pairs_valid_kernel(const float* __restrict__ x, const long long* __restrict__ perm, const long long* __restrict__ gids, float ca,
+                                       float cb, float* __restrict__ out, int B, long long row) {
+  const long long total = (long long)B * row;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / row, e = t - i * row;
+    const float v = x[t];
+    out[t] = gids[i] != -1 ? __fadd_rn(__fmul_rn(ca, v), __fmul_rn(cb, x[perm[i] * row + e])) : v;
+  }
+}
+
 }  // namespace
+
+extern "C" int lnx_cutmix_paste(const float* x, const int64_t* perm, const int64_t* group_ids, float* out, int B, int C, int H, int W, int h1,
+                                int w1, int h2, int w2, lnx_stream_t s) {
+  LNX_REQUIRE(x && perm && group_ids && out, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, LNX_ERR_SHAPE);
+  LNX_REQUIRE(x != out, LNX_ERR_UNSUPPORTED);
+  cudaStream_t st = (cudaStream_t)s;
+  const bool vec = W % 4 == 0 && lnx_aligned16(x) && lnx_aligned16(out);
+  const long long img = (long long)C * H * W, img_v = vec ? img / 4 : img;
+  const int bx = (int)max(1LL, min((img_v + 255) / 256, (long long)(8 * kNumSMs + B - 1) / B));
+  dim3 grid(bx, B);
+  if (vec) cutmix_paste_kernel<4><<<grid, 256, 0, st>>>(x, (const long long*)perm, (const long long*)group_ids, out, img_v, H, W, h1, w1, h2, w2);
+  else cutmix_paste_kernel<1><<<grid, 256, 0, st>>>(x, (const long long*)perm, (const long long*)group_ids, out, img_v, H, W, h1, w1, h2, w2);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+extern "C" int lnx_mix_pairs_valid(const float* x, const int64_t* perm, const int64_t* group_ids, float coef_self, float coef_partner, float* out,
+                                   int B, int64_t row, lnx_stream_t s) {
+  LNX_REQUIRE(x && perm && group_ids && out, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && row > 0, LNX_ERR_SHAPE);
+  LNX_REQUIRE(x != out, LNX_ERR_UNSUPPORTED);
+  const long long total = (long long)B * row;
+  const int blocks = (int)max(1LL, min((total + 255) / 256, (long long)kNumSMs * 16));
+  mix_pairs_valid_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(x, (const long long*)perm, (const long long*)group_ids, coef_self, coef_partner, out, B,
+                                                              row);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
 
 extern "C" int lnx_mix_pairs(const float* x, const int64_t* perm, const float* lam, float* out, int B, int64_t row, lnx_stream_t s) {
   LNX_REQUIRE(x && perm && lam && out, LNX_ERR_NULL);

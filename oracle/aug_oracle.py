@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["exclude_null_group_ids", "enforce_all_or_nothing", "mixup_apply", "is_ingroup_permutation"]
+__all__ = ["exclude_null_group_ids", "enforce_all_or_nothing", "mixup_apply", "cutmix_apply", "rand_bbox_from", "is_ingroup_permutation"]
 
 
 def exclude_null_group_ids(targets: dict, group_ids: np.ndarray, null_task_keys=None) -> np.ndarray:
@@ -69,6 +69,58 @@ def mixup_apply(images, targets: dict, aux, mask, perm, lam, pick, chunk_bounds=
             else:
                 continue
             oa[i, lo:hi], om[i, lo:hi] = src[0][i, lo:hi], src[1][i, lo:hi]
+    return mi, mt, oa, om
+
+
+def _mix_meta(aux, mask, perm, pick, bounds):
+    enforce_all_or_nothing(aux, mask, bounds)
+    a2, m2 = aux[perm], mask[perm]
+    oa, om = np.zeros_like(aux), np.zeros_like(mask)
+    for i in range(aux.shape[0]):
+        for lo, hi in bounds:
+            z1, z2 = bool(np.all(aux[i, lo:hi] == 0.0)), bool(np.all(a2[i, lo:hi] == 0.0))
+            if not z1 and not z2:
+                src = (aux, mask) if pick[i] < 0.5 else (a2, m2)
+            elif not z1:
+                src = (aux, mask)
+            elif not z2:
+                src = (a2, m2)
+            else:
+                continue
+            oa[i, lo:hi], om[i, lo:hi] = src[0][i, lo:hi], src[1][i, lo:hi]
+    return oa, om
+
+
+def rand_bbox_from(size, lam: float, cx: int, cy: int):
+    """R/aug/utils.py:16-43 with the two ``random.randint`` draws (centre) given."""
+    import math
+
+    W, H = size[2], size[3]
+    cut_rat = math.sqrt(1.0 - lam)
+    cut_w, cut_h = int(W * cut_rat), int(H * cut_rat)
+    return max(0, cx - cut_w // 2), max(0, cy - cut_h // 2), min(W, cx + cut_w // 2), min(H, cy + cut_h // 2)
+
+
+def cutmix_apply(images, targets: dict, aux, mask, group_ids, perm, box, pick, chunk_bounds=None):
+    """R/aug/gpu/selective_cutmix.py:204-437 for given draws: box = (bbx1, bby1, bbx2, bby2) over dims 2 / 3; samples with group
+    id != -1 take their partner's pixels inside the box and blend targets with the Python-float lam_adjusted (cast to fp32 the
+    way torch casts a Python scalar operand); metadata as in mixup.  ``aux`` / ``mask`` are enforced in place."""
+    images = np.asarray(images, dtype=np.float32)
+    B, C, H, W = images.shape
+    perm = np.asarray(perm)
+    x1, y1, x2, y2 = box
+    lam_adj = 1.0 - ((x2 - x1) * (y2 - y1)) / (H * W)
+    ca, cb = np.float32(lam_adj), np.float32(1 - lam_adj)
+    valid = np.nonzero(np.asarray(group_ids) != -1)[0]
+    mi = images.copy()
+    mt = {k: np.asarray(v, dtype=np.float32).copy() for k, v in targets.items()}
+    if len(valid):
+        mi[valid, :, x1:x2, y1:y2] = images[perm[valid], :, x1:x2, y1:y2]
+        for k, v in targets.items():
+            v = np.asarray(v, dtype=np.float32)
+            mt[k][valid] = (ca * v[valid]).astype(np.float32) + (cb * v[perm[valid]]).astype(np.float32)
+    D = aux.shape[1]
+    oa, om = _mix_meta(aux, mask, perm, pick, list(chunk_bounds) if chunk_bounds is not None else [(0, D)])
     return mi, mt, oa, om
 
 

@@ -132,6 +132,74 @@ def test_reference_rng_mode_replays_the_reference_draw_sequence():
     assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(ma.cpu().numpy(), oa) and np.array_equal(mm.cpu().numpy(), om)
 
 
+@pytest.mark.parametrize("name", ["aug_three_chunks", "aug_single_chunk"])
+def test_cutmix_apply_matches_reference_golden(name):
+    A = _A()
+    c, g = make_case(name), load_golden(name.replace("aug_", "cutmix_"))
+    images, targets = _t(c["images"]), {k: _t(v) for k, v in c["targets"].items()}
+    aux, masks = _t(c["aux"]), _t(c["masks"])
+    mi, mt, ma, mm = A.cutmix_apply(images, targets, aux, masks, _t(g["eff_gids"]), _t(g["perm"]), tuple(int(v) for v in g["box"]), _t(g["pick"]),
+                                    c["chunks"])
+    assert np.array_equal(mi.cpu().numpy(), g["mixed_images"])
+    for k in targets:
+        assert np.array_equal(mt[k].cpu().numpy(), g["mixed_targets." + k])
+    assert np.array_equal(ma.cpu().numpy(), g["mixed_aux"]) and np.array_equal(mm.cpu().numpy(), g["mixed_masks"])
+    assert np.array_equal(aux.cpu().numpy(), g["aux_after"]) and np.array_equal(masks.cpu().numpy(), g["masks_after"])
+
+
+@pytest.mark.parametrize("B,H,W,box", [(5, 7, 9, (2, 3, 6, 8)), (64, 32, 32, (0, 0, 32, 32)), (33, 16, 20, (5, 5, 5, 9)), (8, 224, 224, (17, 50, 201, 199))])
+def test_cutmix_apply_bit_exact_vs_oracle(B, H, W, box):
+    """Odd widths (scalar path), boxes that split a float4, full-image and empty boxes, ungrouped samples."""
+    A = _A()
+    rng = np.random.default_rng(B + H)
+    images = rng.standard_normal((B, 3, H, W)).astype(np.float32)
+    targets = {"taxa_L10": rng.random((B, 6)).astype(np.float32)}
+    aux = rng.standard_normal((B, 15)).astype(np.float32)
+    aux[rng.random((B, 15)) < 0.15] = 0.0
+    masks = aux != 0
+    gids = rng.integers(0, 3, size=B).astype(np.int64)
+    gids[rng.random(B) < 0.3] = -1
+    perm = np.arange(B)
+    for gid in (0, 1, 2):  # an in-group permutation
+        idx = np.nonzero(gids == gid)[0]
+        perm[idx] = rng.permutation(idx)
+    pick = rng.random(B).astype(np.float32)
+    chunks = [(0, 2), (2, 5), (5, 15)]
+    a_dev, m_dev = _t(aux), _t(masks)
+    mi, mt, ma, mm = A.cutmix_apply(_t(images), {k: _t(v) for k, v in targets.items()}, a_dev, m_dev, _t(gids), _t(perm), box, _t(pick), chunks)
+    a_ref, m_ref = aux.copy(), masks.copy()
+    oi, ot, oa, om = AO.cutmix_apply(images, targets, a_ref, m_ref, gids, perm, box, pick, chunks)
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mt["taxa_L10"].cpu().numpy(), ot["taxa_L10"])
+    assert np.array_equal(ma.cpu().numpy(), oa) and np.array_equal(mm.cpu().numpy(), om)
+    assert np.array_equal(a_dev.cpu().numpy(), a_ref) and np.array_equal(m_dev.cpu().numpy(), m_ref)
+
+
+def test_cutmix_class_device_mode():
+    """GPUSelectiveCutMix (rng='device'): a box is drawn, grouped samples receive their partner's pixels inside it and nothing
+    else changes; PROB = 0 returns the batch untouched."""
+    import random
+
+    A = _A()
+    c = make_case("aug_three_chunks")
+    mk = lambda: (_t(c["images"]), {k: _t(v) for k, v in c["targets"].items()}, _t(c["aux"]), _t(c["masks"]), _t(c["group_ids"]))
+    torch.manual_seed(3)
+    random.seed(3)
+    mix = A.GPUSelectiveCutMix({"PROB": 1.0, "ALPHA": 1.0, "MINMAX": [0.3, 0.7], "meta_chunk_bounds_list": list(c["chunks"])})
+    batch = mk()
+    mi, mt, ma, mm = mix(batch)
+    eff = AO.exclude_null_group_ids(c["targets"], c["group_ids"])
+    perm, box = mix.last_permutation.cpu().numpy(), mix.last_box
+    assert AO.is_ingroup_permutation(perm, eff)
+    ref = c["images"].copy()
+    v = np.nonzero(eff != -1)[0]
+    ref[v, :, box[0]:box[2], box[1]:box[3]] = c["images"][perm[v], :, box[0]:box[2], box[1]:box[3]]
+    assert np.array_equal(mi.cpu().numpy(), ref)
+    off = A.GPUSelectiveCutMix({"PROB": 0.0, "ALPHA": 1.0})
+    batch = mk()
+    out = off(batch)
+    assert out[0] is batch[0] and out[2] is batch[2]
+
+
 def test_aug_rejects_cpu_tensors():
     A = _A()
     with pytest.raises(RuntimeError):

@@ -33,3 +33,15 @@ def test_aug_oracle_chunk_rules():
     assert om.all()
     assert not AO.is_ingroup_permutation(np.array([1, 0, 2]), np.array([0, 1, 1]))
     assert AO.is_ingroup_permutation(np.array([0, 2, 1]), np.array([-1, 1, 1]))
+
+
+@pytest.mark.parametrize("name", ["aug_three_chunks", "aug_single_chunk"])
+def test_cutmix_oracle_reproduces_reference_golden(name):
+    c, g = make_case(name), load_golden(name.replace("aug_", "cutmix_"))
+    aux, masks = c["aux"].copy(), c["masks"].copy()
+    mi, mt, ma, mm = AO.cutmix_apply(c["images"], c["targets"], aux, masks, g["eff_gids"], g["perm"], tuple(g["box"]), g["pick"], c["chunks"])
+    assert np.array_equal(mi, g["mixed_images"])
+    for k in c["targets"]:
+        assert np.array_equal(mt[k], g["mixed_targets." + k])
+    assert np.array_equal(ma, g["mixed_aux"]) and np.array_equal(mm, g["mixed_masks"])
+    assert np.array_equal(aux, g["aux_after"]) and np.array_equal(masks, g["masks_after"])
