@@ -29,7 +29,7 @@ FWD_GFLOP = {"sm": 8.659, "md": 12.505, "xl": 448.16}  # per image (SURVEY.md se
 FWD_GFLOP_V0 = {"sm": 8.94}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (profiles/r01_kernels_summary.md),
 # keyed by (arch, variant, per-GPU batch, image size, dtype); None when that exact shape was not captured
-NCU_TRAFFIC_BYTES = {("v1", "sm", 256, 224, "bf16"): 154.3e6 + 1175.4e6}  # rows 0-1 of r01_kernels_summary.md
+NCU_TRAFFIC_BYTES = {("v1", "sm", 256, 224, "bf16"): 154.3e6 + 1174.6e6}  # rows 0-1 of r01_kernels_summary.md
 
 
 def parse():
