@@ -152,6 +152,14 @@ def cpu_infer_baseline(variant: str, img: int, batch: int, steps: int = 5, warmu
 
 
 # ----------------------------------------------------------------------------- reference arm
+def workload_name(args) -> str:
+    """One name for both arms (the driver pairs their lines by metric and config)."""
+    S = args.img
+    if args.mode == "train":
+        return f"mFormerV1_{args.variant} train step (fwd+6-rank CE loss+bwd+clip+AdamW) {S}x{S}, 3 meta comps, random init"
+    return f"mFormer{args.arch.upper()}_{args.variant} inference (eval forward, 6 rank heads) {S}x{S}, 3 meta comps, random init"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -170,8 +178,8 @@ def run_reference(args):
         "impl": "reference",
         "metric": metric, "value": val, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"mFormer{args.arch.upper()}_{args.variant} {args.mode} step {args.img}x{args.img}, 6 ranks, 3 meta comps (host CPU, oracle port)",
-                   "per_gpu_batch": args.batch, "cpu_sample_batch": b},
+        "config": {"workload": workload_name(args), "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus,
+                   "parallelism": f"dp{args.gpus}", "reference_arm": "host CPU, oracle port of the reference path, fp32", "cpu_sample_batch": b},
         "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of batch {b} (median), {args.warmup} warm-up; oracle/mformer_oracle.py (fp32, torch CPU ops)"},
         "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -386,9 +394,7 @@ def run_b200(args):
         "metric": metric, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": (f"mFormerV1_{args.variant} train step (fwd+6-rank CE loss+bwd+clip+AdamW) {S}x{S}, 3 meta comps, random init"
-                                if args.mode == "train" else
-                                f"mFormer{args.arch.upper()}_{args.variant} inference (eval forward, 6 rank heads) {S}x{S}, 3 meta comps, random init"),
+        "config": {"workload": workload_name(args),
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
                    "l2_policy": ("inputs+activations per step exceed the 126 MB L2; no explicit flush" if l2_flush is None
                                  else "256 MB fill between timed iterations (working set fits in L2); per-iteration CUDA events"),
