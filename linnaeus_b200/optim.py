@@ -107,25 +107,58 @@ class FlatAdamW(torch.optim.Optimizer):
                  None if self._lr_dev is None else self._lr_dev.data_ptr(), self._step_dev.data_ptr())
         return None
 
-    # checkpoint interchange: expose torch.optim.AdamW-shaped state
+    # checkpoint interchange (R/utils/checkpoint.py:956-1200 saves ``optimizer.state_dict()`` of a torch.optim.AdamW, :738-953
+    # loads it back): the state dict has torch.optim.AdamW's shape - per parameter index ``step`` / ``exp_avg`` / ``exp_avg_sq``
+    # in param_groups order - so a reference checkpoint resumes here and one written here resumes in the reference.
     def state_dict(self):
         sd = super().state_dict()
-        sd["flat_step"] = self._step
-        sd["flat_m"] = [f.m.clone() if f is not None else None for f in self.flat]
-        sd["flat_v"] = [f.v.clone() if f is not None else None for f in self.flat]
+        state = {}
+        if self._step > 0:
+            idx = 0
+            for g, f in zip(self.param_groups, self.flat):
+                for i, p in enumerate(g["params"]):
+                    lo, hi = f.span(i)
+                    n = p.numel()
+                    state[idx] = {"step": torch.tensor(float(self._step)), "exp_avg": f.m[lo:lo + n].view_as(p).clone(),
+                                  "exp_avg_sq": f.v[lo:lo + n].view_as(p).clone()}
+                    idx += 1
+        sd["state"] = state
         return sd
 
     def load_state_dict(self, sd):
         sd = dict(sd)
-        self._step = sd.pop("flat_step", 0)
-        self._step_dev.fill_(float(self._step))
-        ms, vs = sd.pop("flat_m", None), sd.pop("flat_v", None)
-        super().load_state_dict(sd)
-        if ms is not None:
-            for f, m, v in zip(self.flat, ms, vs):
+        legacy_m, legacy_v = sd.pop("flat_m", None), sd.pop("flat_v", None)  # round-1 development format
+        legacy_step = sd.pop("flat_step", None)
+        state = sd.get("state", {})
+        super().load_state_dict({"state": {}, "param_groups": sd["param_groups"]})  # hyper-parameters; validates the group layout
+        if legacy_m is not None:
+            self._step = int(legacy_step or 0)
+            for f, m, v in zip(self.flat, legacy_m, legacy_v):
                 if f is not None:
                     f.m.copy_(m)
                     f.v.copy_(v)
+        else:
+            steps = set()
+            idx = 0
+            for g, f in zip(self.param_groups, self.flat):
+                for i, p in enumerate(g["params"]):
+                    st = state.get(idx, state.get(str(idx)))
+                    lo, _ = f.span(i)
+                    n = p.numel()
+                    if st is None:  # torch leaves parameters that never received a gradient without state
+                        f.m[lo:lo + n].zero_()
+                        f.v[lo:lo + n].zero_()
+                    else:
+                        if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                            raise ValueError(f"optimizer state {idx}: shape {tuple(st['exp_avg'].shape)} != parameter shape {tuple(p.shape)}")
+                        f.m[lo:lo + n].copy_(st["exp_avg"].reshape(-1))
+                        f.v[lo:lo + n].copy_(st["exp_avg_sq"].reshape(-1))
+                        steps.add(int(float(st["step"])))
+                    idx += 1
+            if len(steps) > 1:
+                raise ValueError(f"FlatAdamW keeps one step count for all parameters; the state dict has {sorted(steps)}")
+            self._step = steps.pop() if steps else 0
+        self._step_dev.fill_(float(self._step))
 
 
 def build_optimizer(config, model) -> FlatAdamW:

@@ -344,6 +344,66 @@ def test_flat_adamw_matches_torch():
         assert rel_err(ps[n], ref[n]) < 1e-5
 
 
+def test_flat_adamw_state_dict_interchanges_with_torch_adamw(tmp_path):
+    """FlatAdamW.state_dict() has torch.optim.AdamW's layout (R/utils/checkpoint.py saves / loads that): after two steps each
+    side loads the OTHER side's state dict (through a checkpoint file), takes two more steps, and the parameters still agree."""
+    from linnaeus_b200 import checkpoint as C
+    from linnaeus_b200.optim import FlatAdamW
+
+    torch.manual_seed(4)
+    shapes = {"a.weight": (33, 17), "a.bias": (33,), "b.weight": (5, 33), "norm.weight": (33,), "tok": (1, 1, 7)}
+    grads = [{n: torch.randn(s, device=DEV) for n, s in shapes.items()} for _ in range(4)]
+
+    class Holder(torch.nn.Module):
+        def __init__(self, init):
+            super().__init__()
+            self.ps = torch.nn.ParameterDict({n.replace(".", "_"): torch.nn.Parameter(v.clone()) for n, v in init.items()})
+
+    init = {n: torch.randn(s, device=DEV) for n, s in shapes.items()}
+
+    def make_flat(h):
+        return FlatAdamW([(n, h.ps[n.replace(".", "_")]) for n in shapes], lr=3e-3, weight_decay=0.05)
+
+    def make_torch(h):
+        decay = [h.ps[n.replace(".", "_")] for n in ("a.weight", "b.weight", "tok")]
+        nodecay = [h.ps[n.replace(".", "_")] for n in ("a.bias", "norm.weight")]
+        return torch.optim.AdamW([{"params": decay}, {"params": nodecay, "weight_decay": 0.0}], lr=3e-3, weight_decay=0.05)
+
+    def run(h, opt, steps):
+        for g in steps:
+            opt.zero_grad()
+            for n in shapes:
+                p = h.ps[n.replace(".", "_")]
+                if p.grad is None:
+                    p.grad = g[n].clone()
+                else:
+                    p.grad.add_(g[n])
+            opt.step()
+
+    hf, ht = Holder(init), Holder(init)
+    of, ot = make_flat(hf), make_torch(ht)
+    assert of.state_dict()["state"] == {}  # like torch before the first step
+    run(hf, of, grads[:2])
+    run(ht, ot, grads[:2])
+    sdf = of.state_dict()
+    assert set(sdf) == {"state", "param_groups"} and set(sdf["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert [len(g["params"]) for g in sdf["param_groups"]] == [3, 2] and float(sdf["state"][4]["step"]) == 2.0
+    C.save_checkpoint(str(tmp_path / "flat"), hf, of, epoch=1)
+    C.save_checkpoint(str(tmp_path / "torch"), ht, ot, epoch=1)
+    # cross-load: the torch-written file resumes a FlatAdamW run and vice versa
+    hf2, ht2 = Holder(init), Holder(init)
+    of2, ot2 = make_flat(hf2), make_torch(ht2)
+    C.load_checkpoint(str(tmp_path / "torch" / "latest.pth"), hf2, of2, map_location=DEV)
+    C.load_checkpoint(str(tmp_path / "flat" / "latest.pth"), ht2, ot2, map_location=DEV)
+    run(hf2, of2, grads[2:])
+    run(ht2, ot2, grads[2:])
+    run(hf, of, grads[2:])
+    for n in shapes:
+        k = n.replace(".", "_")
+        assert rel_err(hf2.ps[k], ht2.ps[k]) < 1e-5
+        assert rel_err(hf2.ps[k], hf.ps[k]) < 1e-5  # resumed == uninterrupted
+
+
 def test_aggregate_and_colsum():
     F = _F()
     a = torch.randn(9, 40, device=DEV, requires_grad=True)

@@ -1,0 +1,53 @@
+"""CPU: checkpoint plumbing (file names, keys, module. prefix, auto-resume) against the reference's conventions
+(R/utils/checkpoint.py:21-42, 1028-1131, 1307-1332)."""
+import os
+import time
+
+import pytest
+import torch
+
+from linnaeus_b200 import checkpoint as C
+from tests.support import refload
+
+
+def test_prefix_cleaning_matches_reference():
+    sd = {"a.weight": 1, "b.bias": 2}
+    pre = {"module.a.weight": 1, "module.b.bias": 2}
+    assert C.clean_state_dict_keys(sd, True, False) == pre
+    assert C.clean_state_dict_keys(pre, False, True) == sd
+    assert C.clean_state_dict_keys(sd, False, False) == sd and C.clean_state_dict_keys(pre, True, True) == pre
+    if refload.reference_available():
+        refload.import_reference()
+        from linnaeus.utils.checkpoint import _clean_state_dict_keys
+
+        for d, ddp, has in ((sd, True, False), (pre, False, True), (sd, False, False), (pre, True, True), ({"module.x": 1, "y": 2}, False, True)):
+            assert C.clean_state_dict_keys(d, ddp, has) == _clean_state_dict_keys(d, ddp, has)
+
+
+def test_save_load_roundtrip_and_auto_resume(tmp_path):
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.LayerNorm(3))
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    net(torch.randn(2, 4)).sum().backward()
+    opt.step()
+    assert C.auto_resume_helper(str(tmp_path)) is None
+    p1 = C.save_checkpoint(str(tmp_path), net, opt, epoch=1, config={"k": 1}, iteration=7)
+    assert os.path.basename(p1) == "ckpt_epoch_1.pth" and os.path.exists(tmp_path / "latest.pth")
+    ck = torch.load(p1, weights_only=False)
+    assert set(ck) == {"model", "optimizer", "lr_scheduler", "epoch", "config", "iteration"}  # the reference's core keys
+    time.sleep(0.02)
+    p2 = C.save_checkpoint(str(tmp_path), net, opt, epoch=2, extra={"wandb_run_id": "r"})
+    os.utime(p2, (time.time() + 5, time.time() + 5))
+    assert C.auto_resume_helper(str(tmp_path)) == p2
+    # a DDP-prefixed file loads into a bare model
+    ck["model"] = {f"module.{k}": v for k, v in ck["model"].items()}
+    torch.save(ck, tmp_path / "ddp.pth")
+    net2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.LayerNorm(3))
+    opt2 = torch.optim.AdamW(net2.parameters(), lr=5e-2)
+    rest = C.load_checkpoint(str(tmp_path / "ddp.pth"), net2, opt2)
+    assert rest["epoch"] == 1 and rest["iteration"] == 7 and rest["config"] == {"k": 1}
+    for a, b in zip(net.state_dict().values(), net2.state_dict().values()):
+        assert torch.equal(a, b)
+    assert opt2.param_groups[0]["lr"] == 1e-3
+    with pytest.raises(RuntimeError):
+        C.load_checkpoint(p1, torch.nn.Linear(4, 3))
