@@ -14,6 +14,8 @@
 // seven compute warps work on the current one.  There is no CTA-wide barrier in the steady state: buffers are
 // handed over with full / empty mbarriers, so compute warps drift freely by up to one tile.  The weight-gradient kernel keeps 49 fp32x2
 // partial sums per lane in registers across all tiles the CTA visits.
+#include <stdlib.h>
+
 #include "lnx_common.cuh"
 #include "lnx_tc_common.cuh"
 
@@ -50,20 +52,21 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_w, int tiles_h)
 }
 
 // ------------------------------------------------------------------ forward (and data gradient with flipped taps)
-__global__ void __launch_bounds__(NTHREADS, 3)
+template <int NS>  // halo-tile ring depth: 2 (three CTAs per SM) or 3 (two CTAs per SM; a full tile of compute between load and use)
+__global__ void __launch_bounds__(NTHREADS, NS == 2 ? 3 : 2)
     dwconv7_fwd_x2_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w49c, const float* __restrict__ bias,
                           const bf16* __restrict__ res, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* tiles = smem_raw;                                              // [2][20][20][CC] bf16
-  float2* wsm = reinterpret_cast<float2*>(smem_raw + 2 * HALO_BYTES);           // [49][PW]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * HALO_BYTES + 49 * CC * 4);  // [2]
-  uint64_t* empty = full + 2;                                                   // [2]
+  float2* wsm = reinterpret_cast<float2*>(smem_raw + NS * HALO_BYTES);           // [49][PW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NS * HALO_BYTES + 49 * CC * 4);  // [NS]
+  uint64_t* empty = full + NS;                                                  // [NS]
 
   const int c0 = blockIdx.y * CC;
   const int total = B * tiles_h * tiles_w;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NS; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], NWARPS);
     }
@@ -78,8 +81,8 @@ __global__ void __launch_bounds__(NTHREADS, 3)
     if (lane == 0) {
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait_relaxed(&empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const int buf = it % NS;
+        mbar_wait_relaxed(&empty[buf], (((uint32_t)it / NS) & 1u) ^ 1u);
         const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
         mbar_expect_tx(&full[buf], HALO_BYTES);
         tma_load_4d(tiles + buf * HALO_BYTES, &tmX, &full[buf], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
@@ -95,9 +98,9 @@ __global__ void __launch_bounds__(NTHREADS, 3)
 
   int it = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-    const int buf = it & 1;
+    const int buf = it % NS;
     const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
-    mbar_wait(&full[buf], ((uint32_t)it >> 1) & 1u);
+    mbar_wait(&full[buf], ((uint32_t)it / NS) & 1u);
 
     float2 acc[2][7];
     if (tc.h0 + orow0 < H) {
@@ -271,17 +274,22 @@ int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, co
   CUtensorMap tmX;
   if (!make_nhwc_tmap(&tmX, x, B, H, W, C, HALO, HALO)) return LNX_ERR_UNSUPPORTED;
   const int tiles_w = (W + TILE - 1) / TILE, tiles_h = (H + TILE - 1) / TILE;
-  const size_t smem = 2 * HALO_BYTES + 49 * CC * 4 + 64;
+  static const int ns = getenv("LNX_DWCONV_STAGES") ? atoi(getenv("LNX_DWCONV_STAGES")) : 2;
+  const size_t smem = (size_t)(ns == 3 ? 3 : 2) * HALO_BYTES + 49 * CC * 4 + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv7_fwd_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ns == 3 ? cudaFuncSetAttribute(dwconv7_fwd_x2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(dwconv7_fwd_x2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return lnx_set_cuda_error(e);
     attr_set = true;
   }
   const int chunks = C / CC;
   const int total = B * tiles_h * tiles_w;
-  const int gx = max(1, min(total, (kNumSMs * 3 + chunks - 1) / chunks));
-  dwconv7_fwd_x2_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
+  const int gx = max(1, min(total, (kNumSMs * (ns == 3 ? 2 : 3) + chunks - 1) / chunks));
+  if (ns == 3)
+    dwconv7_fwd_x2_kernel<3><<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
+  else
+    dwconv7_fwd_x2_kernel<2><<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
