@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import loss as LL
+from .flat import weights_changed
 from .optim import FlatAdamW
 from .parallel import DataParallel
 
@@ -141,6 +142,7 @@ class TrainStep:
             for k, v in targets.items():
                 st[k].copy_(v, non_blocking=True)
         self._graph.replay()
+        weights_changed()  # the captured optimizer kernel rewrote the parameters; no host-side step() ran to say so
         if self.dp is not None:
             self.dp.finish_gradients()
             self.opt.step()

@@ -7,6 +7,15 @@ from __future__ import annotations
 
 import torch
 
+# Bumped by everything that rewrites parameter memory WITHOUT going through a torch op on the parameter tensor itself (the fused
+# AdamW kernel, the data-parallel broadcast of the flat buffer): such writes do not advance ``param._version``, and the cached
+# bf16 weights of the inference path (mformer_v1._Bf16Shadow) key on this counter together with the parameter versions.
+WEIGHTS_EPOCH = [0]
+
+
+def weights_changed() -> None:
+    WEIGHTS_EPOCH[0] += 1
+
 
 class FlatGroup:
     def __init__(self, params: list[torch.nn.Parameter], with_state: bool = True):
@@ -29,6 +38,7 @@ class FlatGroup:
                     self.g[o:o + n].copy_(p.grad.reshape(-1))
                 p.data = self.p[o:o + n].view(p.shape)
                 p.grad = self.g[o:o + n].view(p.shape)
+        weights_changed()
 
     def span(self, i: int) -> tuple[int, int]:
         return self.offsets[i], self.offsets[i] + self.params[i].numel()

@@ -50,17 +50,31 @@ def _wc(p: torch.Tensor):
     return None if _ACTIVE_SHADOW is None else _ACTIVE_SHADOW.get(id(p))
 
 
+from .flat import WEIGHTS_EPOCH  # noqa: E402
+
+
 class _Bf16Shadow:
     """bf16 copies of all parameters, refreshed with one cast launch per distinct storage: after FlatAdamW has
     re-homed the parameters that is two launches per step instead of one per weight."""
 
     def __init__(self):
         self.key = None
+        self.stamp = None
         self.bufs = []   # (fp32 storage-wide view, bf16 buffer)
         self.views = {}
 
-    def refresh(self, params) -> dict:
+    def refresh(self, params, reuse_if_unchanged: bool = False) -> dict:
+        """``reuse_if_unchanged`` (inference: grad mode off): skip the casts when no parameter was written since the last refresh -
+        same storages, same ``_version`` of every parameter, same flat.WEIGHTS_EPOCH (kernel-side writes).  Without FlatAdamW every
+        weight has its own storage, i.e. ~90 cast launches per forward otherwise."""
         key = tuple(p.data_ptr() for p in params)
+        if reuse_if_unchanged:
+            stamp = (key, tuple(p._version for p in params), WEIGHTS_EPOCH[0])
+            if stamp == self.stamp:
+                return self.views
+        else:
+            stamp = None
+        self.stamp = stamp
         if key != self.key:
             by_storage = {}
             for p in params:
@@ -402,7 +416,7 @@ class mFormerV1(nn.Module):
                     if self._shadow is None:
                         self._shadow = _Bf16Shadow()
                         self._shadow_params = [p for p in self.parameters() if p.ndim >= 2]
-                    _ACTIVE_SHADOW = self._shadow.refresh(self._shadow_params)
+                    _ACTIVE_SHADOW = self._shadow.refresh(self._shadow_params, reuse_if_unchanged=not torch.is_grad_enabled())
                 else:
                     _ACTIVE_SHADOW = None
                 return self._features(x, meta, cd)

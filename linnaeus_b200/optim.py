@@ -16,7 +16,7 @@ import math
 import torch
 
 from ._lib import call
-from .flat import FlatGroup
+from .flat import FlatGroup, weights_changed
 
 
 def split_decay(named_params) -> tuple[list, list]:
@@ -105,6 +105,7 @@ class FlatAdamW(torch.optim.Optimizer):
             call("lnx_adamw", f.p.data_ptr(), f.g.data_ptr(), f.m.data_ptr(), f.v.data_ptr(), f.numel, float(g["lr"]), float(b1), float(b2),
                  float(g["eps"]), float(g["weight_decay"]), 1.0 - b1 ** t, 1.0 - b2 ** t, self.grad_scale, sc[2:].data_ptr(),
                  None if self._lr_dev is None else self._lr_dev.data_ptr(), self._step_dev.data_ptr())
+        weights_changed()  # the kernel wrote the parameters behind torch's version counters
         return None
 
     # checkpoint interchange (R/utils/checkpoint.py:956-1200 saves ``optimizer.state_dict()`` of a torch.optim.AdamW, :738-953

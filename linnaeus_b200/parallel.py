@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .flat import FlatGroup
+from .flat import FlatGroup, weights_changed
 
 
 class _Bucket:
@@ -82,6 +82,7 @@ class DataParallel(nn.Module):
         if self.world > 1:
             for g in self.groups:
                 dist.broadcast(g.p, src=0, group=self.pg)
+        weights_changed()
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)

@@ -181,3 +181,54 @@ def test_cpu_input_fails_loudly():
     L, O, cfg, nc, kind, z, a, P, x, meta, tg, model = _setup("tiny_ce")
     with pytest.raises(RuntimeError):
         model(x, meta)
+
+
+def test_inference_weight_cache_never_goes_stale():
+    """The eval forward caches the bf16 copies of the weights; every way the weights can change must invalidate it: an eager
+    optimizer step, a CUDA-graph replay of the train step (the optimizer kernel runs without any host-side call), load_state_dict."""
+    import linnaeus_b200 as L
+    from linnaeus_b200 import loss as LL
+    from linnaeus_b200.engine import TrainStep
+    from linnaeus_b200.optim import FlatAdamW
+
+    torch.manual_seed(0)
+    cfg, nc = L.make_synthetic_config("sm", 64, dims=(32, 64, 128, 256), heads=(2, 4), rope_depths=(1, 1), conv_depths=(1, 1, 1, 1), n_tasks=2)
+    model = L.build_model(cfg, nc).to(DEV).set_compute_dtype(torch.bfloat16)
+    keys = list(nc.keys())
+    x, meta = torch.randn(4, 3, 64, 64, device=DEV), torch.randn(4, 15, device=DEV)
+    tg = {k: torch.randint(1, nc[k], (4,), device=DEV) for k in keys}
+
+    def infer():
+        model.eval()
+        with torch.no_grad():
+            return torch.cat([v.float() for v in model(x, meta).values()], 1).clone()
+
+    def fresh():  # a grad-enabled forward always re-casts the weights
+        model.eval()
+        return torch.cat([v.float() for v in model(x, meta).values()], 1).detach().clone()
+
+    a0 = infer()
+    assert torch.equal(a0, infer())  # cached path is deterministic
+    opt = FlatAdamW(model.named_parameters(), lr=5e-2, clip_grad=0.0)
+    assert torch.equal(infer(), a0)  # re-homing the parameters into the flat buffer changes nothing
+    ts = TrainStep(model, opt, keys, nc, kind="ce", config=cfg)
+    model.train()
+    ts.step(x, meta, tg)  # eager optimizer step
+    a1 = infer()
+    assert not torch.equal(a1, a0) and torch.equal(a1, fresh())
+    model.train()
+    ts.capture(x, meta, tg)
+    b0 = infer()
+    model.train()
+    ts.replay()  # the optimizer runs inside the graph
+    torch.cuda.synchronize()
+    b1 = infer()
+    assert not torch.equal(b1, b0) and torch.equal(b1, fresh())
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1.5)
+    c0 = infer()
+    assert torch.equal(c0, fresh())
+    model.load_state_dict(sd)
+    assert torch.equal(infer(), b1)
