@@ -232,3 +232,51 @@ def test_inference_weight_cache_never_goes_stale():
     assert torch.equal(c0, fresh())
     model.load_state_dict(sd)
     assert torch.equal(infer(), b1)
+
+
+@pytest.mark.parametrize("with_optimizer", [False, True])
+def test_gradnorm_task_gradient_norms_match_oracle_autograd(with_optimizer):
+    """One forward + K backward passes through the retained graph (linnaeus_b200.gradnorm.task_gradient_norms) against the
+    reference's definition evaluated on the CPU oracle: per task, mean loss over non-null samples with the metadata zeroed, and
+    the L2 norm of torch.autograd.grad w.r.t. the backbone (names without "head" / "meta_")."""
+    import torch.nn.functional as TF
+
+    import linnaeus_b200.loss as LL
+    from linnaeus_b200 import gradnorm as G
+    from linnaeus_b200.optim import FlatAdamW
+
+    L, O, cfg, nc, kind, z, a, P, x, meta, tg, model = _setup("tiny_ce")
+    keys = [t for t, _ in a.tasks]
+    # oracle side
+    leaves = {n: t.clone().requires_grad_(True) for n, t in P.items()}
+    backbone = [n for n in leaves if "head" not in n and "meta_" not in n]
+    ref_loss, ref_norm = {}, {}
+    logits = O.forward(leaves, a, x, torch.zeros_like(meta))
+    for i, k in enumerate(keys):
+        valid = tg[k] != 0
+        lv = TF.cross_entropy(logits[k], tg[k], reduction="none")
+        partial = lv[valid].sum() / max(int(valid.sum()), 1)
+        gs = torch.autograd.grad(partial, [leaves[n] for n in backbone], retain_graph=True, allow_unused=True)
+        ref_loss[k] = float(partial)
+        ref_norm[k] = float(torch.sqrt(sum((g ** 2).sum() for g in gs if g is not None)))
+    # device side
+    model.set_compute_dtype(torch.float32).train()
+    opt = FlatAdamW(model.named_parameters(), lr=1e-3) if with_optimizer else None
+    crit = {k: LL.CrossEntropyLoss() for k in keys}
+    tgd = {k: v.to(DEV) for k, v in tg.items()}
+    losses, norms = G.task_gradient_norms(model, x.to(DEV), meta.to(DEV), tgd, crit, keys, optimizer=opt)
+    for k in keys:
+        assert float(losses[k]) == pytest.approx(ref_loss[k], rel=1e-4)
+        assert float(norms[k]) == pytest.approx(ref_norm[k], rel=1e-4), (k, float(norms[k]), ref_norm[k])
+    assert all(float(p.grad.abs().sum()) == 0.0 for p in model.parameters() if p.grad is not None)  # left zeroed
+    # the whole update through the module, against the same arithmetic fed with the oracle's numbers
+    gn = G.GradNormModule(keys, alpha=1.5)
+    ref = G.GradNormModule(keys, alpha=1.5)
+    m = G.update_gradnorm_weights(gn, model, (x.to(DEV), tgd, meta.to(DEV)), crit, optimizer=opt)
+    ref.measure_and_update({k: torch.tensor(v) for k, v in ref_loss.items()}, {k: torch.tensor(v) for k, v in ref_norm.items()})
+    torch.testing.assert_close(gn.task_weights.cpu(), ref.task_weights, rtol=2e-4, atol=1e-6)
+    assert f"gradnorm/weight/{keys[0]}" in m
+    # a normal training step still works afterwards (the graph of the measurement passes is gone, grads are clean)
+    out, total = _loss(L, O, model, a, kind, x, meta, tg, cfg)
+    total.backward()
+    assert abs(float(total.detach()) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
