@@ -150,17 +150,44 @@ class HierMetricsAccumulator:
         _, counters = hier_metrics(cat, offs, tg, null_index=self.null_index)
         self._rows.append(counters)
 
-    def compute(self) -> dict:
+    def compute(self, all_reduce: bool | None = None, group=None) -> dict:
+        """One device->host read for the phase.  Under ``torch.distributed`` (``all_reduce`` None = "if initialised") the local
+        sums and counts are summed over the ranks before dividing, as ``MetricsTracker._finalize_phase`` does with its accumulators
+        (R/utils/metrics/tracker.py:1112-1136, 1209-1231)."""
         if not self._rows:
+            rows, dev = [], torch.device("cpu")
+        else:
+            rows, dev = torch.stack(self._rows).tolist(), self._rows[0].device  # the phase's only device->host read
+        return self._finalize(rows, self._keys or [], dev, all_reduce, group)
+
+    @staticmethod
+    def _finalize(rows: list, keys: list[str], device, all_reduce: bool | None = None, group=None) -> dict:
+        """rows: per-batch counter rows (lnx_hier_metrics layout).  chain / partial-chain follow the tracker's arithmetic: the sum
+        over batches of (per-batch value x batch size) over the sum of batch sizes (a batch without any non-null sample counts as
+        1.0, chain_accuracy.py:351)."""
+        import torch.distributed as dist
+
+        K = len(keys)
+        if all_reduce is None:
+            all_reduce = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if not rows and not all_reduce:
             return {"acc1": {}, "acc3": {}, "chain_accuracy": 0.0, "partial_chain_accuracy": 0.0, "samples": 0}
-        rows = torch.stack(self._rows).tolist()  # the phase's only device->host read
-        K = len(self._keys)
-        tot = sum(r[2 * K + 3] for r in rows)
-        acc1 = {k: 100.0 * sum(r[i] for r in rows) / tot for i, k in enumerate(self._keys)}
-        acc3 = {k: 100.0 * sum(r[K + i] for r in rows) / tot for i, k in enumerate(self._keys)}
-        chain = sum(r[2 * K] for r in rows) / tot  # sum_b (c_b / B_b) * B_b / sum_b B_b
-        partial = sum((r[2 * K + 1] / r[2 * K + 2] if r[2 * K + 2] > 0 else 1.0) * r[2 * K + 3] for r in rows) / tot
-        return {"acc1": acc1, "acc3": acc3, "chain_accuracy": chain, "partial_chain_accuracy": partial, "samples": tot}
+        local = [0.0] * (2 * K + 3)  # top-1 sums, top-3 sums, chain sum, partial-chain sum, samples
+        for r in rows:
+            for i in range(2 * K):
+                local[i] += r[i]
+            local[2 * K] += r[2 * K]
+            local[2 * K + 1] += (r[2 * K + 1] / r[2 * K + 2] if r[2 * K + 2] > 0 else 1.0) * r[2 * K + 3]
+            local[2 * K + 2] += r[2 * K + 3]
+        if all_reduce:
+            t = torch.tensor(local, dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            local = t.tolist()
+        tot = local[2 * K + 2]
+        if tot <= 0:
+            return {"acc1": {}, "acc3": {}, "chain_accuracy": 0.0, "partial_chain_accuracy": 0.0, "samples": 0}
+        return {"acc1": {k: 100.0 * local[i] / tot for i, k in enumerate(keys)}, "acc3": {k: 100.0 * local[K + i] / tot for i, k in enumerate(keys)},
+                "chain_accuracy": local[2 * K] / tot, "partial_chain_accuracy": local[2 * K + 1] / tot, "samples": int(round(tot))}
 
 
 def topk_predictions(outputs: dict, k: int = 5, keys: list[str] | None = None) -> dict:
