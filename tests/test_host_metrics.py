@@ -48,8 +48,18 @@ def test_finalize_all_reduces_over_ranks():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
+    # spawned children copy sys.path: earlier tests put /root/reference (which has its own `tests` package) in front of it,
+    # and the children must resolve `tests.test_host_metrics` to THIS repository
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    saved = list(sys.path)
+    sys.path.insert(0, repo)
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        sys.path[:] = saved
     res = dict(q.get(timeout=180) for _ in range(2))
     for p in procs:
         p.join(timeout=60)
