@@ -226,9 +226,11 @@ int lnx_attn_bias_fwd(const void* qkv, const float* bias, void* out, int B, int 
  * logits [B, ld] (`dtype`; head k occupies columns class_off[k] .. class_off[k+1], class_off a HOST array of K+1 ints,
  * K <= 16); targets int64 [K, B] (class indices; one-hot / soft targets are arg-maxed by the caller as the reference does).
  * rank[k,i] = #{c : z[c] > z[y] or (z[c] == z[y] and c < y)}  (0 <=> argmax == y; first index wins ties like torch.argmax).
- * ranks_out int32 [K, B] (nullable).  counters int64 [2K+4] (nullable), ADDED to: [0,K) top-1 correct per task; [K,2K) top-3
+ * ranks_out int32 [K, B] (nullable).  counters int64 [4K+4] (nullable), ADDED to: [0,K) top-1 correct per task; [K,2K) top-3
  * correct per task (top-1 when C_k < 3, tracker.py:722-724); [2K] samples with every task right; [2K+1] samples right on
- * tasks 0..highest task whose target != null_index; [2K+2] samples with any target != null_index; [2K+3] samples. */
+ * tasks 0..highest task whose target != null_index; [2K+2] samples with any target != null_index; [2K+3] samples;
+ * [2K+4,3K+4) top-1 correct among samples whose target of that task == null_index, [3K+4,4K+4) their number
+ * (null / non-null accuracy split, tracker.py:786-912). */
 int lnx_hier_metrics(const void* logits, int dtype, int64_t ld, int B, int K, const int* class_off, const int64_t* targets,
                      int null_index, int* ranks_out, int64_t* counters, lnx_stream_t s);
 /* softmax + top-kk per head for the whole batch (R/inference/handler.py:186-214: softmax -> topk -> .item() per sample and

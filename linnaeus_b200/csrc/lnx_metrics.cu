@@ -12,6 +12,8 @@
 //                                                            tracker.py:722-724)
 //     [2K]      chain correct (all K ranks right) [2K + 1]  partial-chain correct (ranks 0..highest non-null right)
 //     [2K + 2]  samples with any non-null target  [2K + 3]  samples
+//     [2K + 4, 3K + 4)  top-1 correct among the samples whose target for that task IS null (tracker.py:797-848)
+//     [3K + 4, 4K + 4)  samples whose target for that task is null (non-null accuracy = the complements)
 // with integer atomics (order independent => bit-reproducible).  HBM traffic = the logits once (B * sum C_k elements).
 #include "lnx_common.cuh"
 
@@ -63,6 +65,10 @@ __global__ void __launch_bounds__(128) hier_metrics_kernel(const T* __restrict__
       const bool top3 = C < 3 ? top1 : s_rank[k] < 3;
       if (top1) atomicAdd(reinterpret_cast<unsigned long long*>(counters + k), 1ULL);
       if (top3) atomicAdd(reinterpret_cast<unsigned long long*>(counters + K + k), 1ULL);
+      if ((int)targets[(long long)k * B + i] == null_index) {
+        if (top1) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2 * K + 4 + k), 1ULL);
+        atomicAdd(reinterpret_cast<unsigned long long*>(counters + 3 * K + 4 + k), 1ULL);
+      }
       chain = chain && top1;
       if (k <= highest) partial = partial && top1;
     }

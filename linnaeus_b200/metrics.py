@@ -53,7 +53,7 @@ def _require_cuda(t: torch.Tensor) -> None:
 def hier_metrics(cat: torch.Tensor, class_off, targets_kb: torch.Tensor, null_index: int = 0, counters: torch.Tensor | None = None,
                  want_ranks: bool = False):
     """Raw ``lnx_hier_metrics`` call.  cat [B, >= class_off[-1]] (f32 / bf16), targets_kb int64 [K, B].  ``counters`` int64
-    [2K+4] is ADDED to (created zeroed when None and ``want_ranks`` is False).  Returns (ranks int32 [K, B] | None, counters)."""
+    [4K+4] is ADDED to (created zeroed when None and ``want_ranks`` is False).  Returns (ranks int32 [K, B] | None, counters)."""
     _require_cuda(cat)
     K = len(class_off) - 1
     B = cat.shape[0]
@@ -62,7 +62,7 @@ def hier_metrics(cat: torch.Tensor, class_off, targets_kb: torch.Tensor, null_in
     targets_kb = targets_kb.to(device=cat.device, dtype=torch.int64).contiguous()
     ranks = torch.empty((K, B), dtype=torch.int32, device=cat.device) if want_ranks else None
     if counters is None and not want_ranks:
-        counters = torch.zeros(2 * K + 4, dtype=torch.int64, device=cat.device)
+        counters = torch.zeros(4 * K + 4, dtype=torch.int64, device=cat.device)
     offs = (ctypes.c_int * (K + 1))(*class_off)
     call("lnx_hier_metrics", cat.data_ptr(), dt(cat), cat.stride(0), B, K, offs, targets_kb.data_ptr(), int(null_index),
          0 if ranks is None else ranks.data_ptr(), 0 if counters is None else counters.data_ptr())
@@ -124,7 +124,8 @@ class HierMetricsAccumulator:
 
     ``update(outputs, targets)`` takes the model's ``{task: logits}`` dict (tasks are ordered by their ``_L<n>`` suffix as the
     tracker does) and the targets dict; ``compute()`` returns ``{"acc1": {task: %}, "acc3": {task: %}, "chain_accuracy": f,
-    "partial_chain_accuracy": f, "samples": n}`` with the tracker's arithmetic: chain / partial-chain are the batch-size
+    "partial_chain_accuracy": f, "samples": n, "null_acc1": {task: %}, "non_null_acc1": {task: %}}`` (null = target index ==
+    ``null_index``; for one-hot targets that is the reference's ``target[:, 0] > 0.5``) with the tracker's arithmetic: chain / partial-chain are the batch-size
     weighted means of the per-batch values (a batch without any non-null sample contributes 1.0, chain_accuracy.py:351)."""
 
     def __init__(self, null_index: int = 0):
@@ -172,13 +173,16 @@ class HierMetricsAccumulator:
             all_reduce = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         if not rows and not all_reduce:
             return {"acc1": {}, "acc3": {}, "chain_accuracy": 0.0, "partial_chain_accuracy": 0.0, "samples": 0}
-        local = [0.0] * (2 * K + 3)  # top-1 sums, top-3 sums, chain sum, partial-chain sum, samples
+        # top-1 sums, top-3 sums, chain sum, partial-chain sum, samples, null-target top-1 sums, null-target counts
+        local = [0.0] * (4 * K + 3)
         for r in rows:
             for i in range(2 * K):
                 local[i] += r[i]
             local[2 * K] += r[2 * K]
             local[2 * K + 1] += (r[2 * K + 1] / r[2 * K + 2] if r[2 * K + 2] > 0 else 1.0) * r[2 * K + 3]
             local[2 * K + 2] += r[2 * K + 3]
+            for i in range(2 * K):
+                local[2 * K + 3 + i] += r[2 * K + 4 + i]
         if all_reduce:
             t = torch.tensor(local, dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -186,8 +190,12 @@ class HierMetricsAccumulator:
         tot = local[2 * K + 2]
         if tot <= 0:
             return {"acc1": {}, "acc3": {}, "chain_accuracy": 0.0, "partial_chain_accuracy": 0.0, "samples": 0}
+        null_ok, null_n = local[2 * K + 3:3 * K + 3], local[3 * K + 3:4 * K + 3]
         return {"acc1": {k: 100.0 * local[i] / tot for i, k in enumerate(keys)}, "acc3": {k: 100.0 * local[K + i] / tot for i, k in enumerate(keys)},
-                "chain_accuracy": local[2 * K] / tot, "partial_chain_accuracy": local[2 * K + 1] / tot, "samples": int(round(tot))}
+                "chain_accuracy": local[2 * K] / tot, "partial_chain_accuracy": local[2 * K + 1] / tot, "samples": int(round(tot)),
+                # tracker.py:1376-1392 / 1463-1479: only tasks that saw such samples get a value
+                "null_acc1": {k: 100.0 * null_ok[i] / null_n[i] for i, k in enumerate(keys) if null_n[i] > 0},
+                "non_null_acc1": {k: 100.0 * (local[i] - null_ok[i]) / (tot - null_n[i]) for i, k in enumerate(keys) if tot - null_n[i] > 0}}
 
 
 def topk_predictions(outputs: dict, k: int = 5, keys: list[str] | None = None) -> dict:

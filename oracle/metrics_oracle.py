@@ -82,10 +82,14 @@ def partial_chain_accuracy(outputs_list, targets_list) -> float:
 
 
 def phase_counters(outputs_list, targets_list, null_index: int = 0) -> np.ndarray:
-    """The int64 [2K+4] counter row one ``lnx_hier_metrics`` call adds (include/linnaeus_b200.h)."""
+    """The int64 [4K+4] counter row one ``lnx_hier_metrics`` call adds (include/linnaeus_b200.h)."""
     eq, gts = _eq_matrix(outputs_list, targets_list)
     B, K = eq.shape
-    c = np.zeros(2 * K + 4, dtype=np.int64)
+    c = np.zeros(4 * K + 4, dtype=np.int64)
+    for k in range(K):  # R/utils/metrics/tracker.py:797-848: top-1 correct and count over the null-target samples of the task
+        is_null = gts[:, k] == null_index
+        c[2 * K + 4 + k] = int(np.sum(eq[:, k] & is_null))
+        c[3 * K + 4 + k] = int(is_null.sum())
     for k, o in enumerate(outputs_list):
         r = target_rank(o, gts[:, k])
         c[k] = int(np.sum(r == 0))
@@ -107,6 +111,8 @@ def phase_metrics(batches, keys) -> dict:
     K = len(keys)
     s1 = np.zeros(K)
     s3 = np.zeros(K)
+    n_ok = np.zeros(K)
+    n_cnt = np.zeros(K)
     chain = partial = tot = 0.0
     for outputs, targets in batches:
         ol = [np.asarray(outputs[k], dtype=np.float32) for k in keys]
@@ -115,11 +121,15 @@ def phase_metrics(batches, keys) -> dict:
         c = phase_counters(ol, tl)
         s1 += c[:K]
         s3 += c[K:2 * K]
+        n_ok += c[2 * K + 4:3 * K + 4]
+        n_cnt += c[3 * K + 4:4 * K + 4]
         chain += chain_accuracy(ol, tl) * B
         partial += partial_chain_accuracy(ol, tl) * B
         tot += B
     return {"acc1": {k: 100.0 * s1[i] / tot for i, k in enumerate(keys)}, "acc3": {k: 100.0 * s3[i] / tot for i, k in enumerate(keys)},
-            "chain_accuracy": chain / tot, "partial_chain_accuracy": partial / tot, "samples": int(tot)}
+            "chain_accuracy": chain / tot, "partial_chain_accuracy": partial / tot, "samples": int(tot),
+            "null_acc1": {k: 100.0 * n_ok[i] / n_cnt[i] for i, k in enumerate(keys) if n_cnt[i] > 0},
+            "non_null_acc1": {k: 100.0 * (s1[i] - n_ok[i]) / (tot - n_cnt[i]) for i, k in enumerate(keys) if tot - n_cnt[i] > 0}}
 
 
 def softmax_topk(logits: np.ndarray, k: int) -> tuple:

@@ -26,6 +26,7 @@ def main():
         K = len(keys)
         rec = {}
         s1, s3 = np.zeros(K), np.zeros(K)
+        nul_ok, nul_n, non_ok, non_n = np.zeros(K), np.zeros(K), np.zeros(K), np.zeros(K)
         chain = partial = tot = 0.0
         for bi, (outputs, targets) in enumerate(batches):
             ol = [torch.from_numpy(outputs[k]) for k in keys]
@@ -41,6 +42,11 @@ def main():
                 c3 = c1 if min(3, C) < 3 else (ol[i].topk(3, dim=1)[1] == tl[i].unsqueeze(1)).any(dim=1).sum().item()
                 s1[i] += c1
                 s3[i] += c3
+                is_null = tl[i] == 0  # tracker.py:797-912 (hard labels)
+                nul_ok[i] += ((preds == tl[i]) & is_null).sum().item()
+                nul_n[i] += is_null.sum().item()
+                non_ok[i] += ((preds == tl[i]) & ~is_null).sum().item()
+                non_n[i] += (~is_null).sum().item()
                 kk = min(5, C)
                 p, ix = torch.topk(torch.softmax(ol[i], dim=-1), k=kk)
                 rec[f"b{bi}.{k}.topk_idx"], rec[f"b{bi}.{k}.topk_prob"] = ix.numpy(), p.numpy()
@@ -51,6 +57,9 @@ def main():
             partial += pa * B
             tot += B
         rec["acc1"], rec["acc3"] = 100.0 * s1 / tot, 100.0 * s3 / tot
+        with np.errstate(invalid="ignore", divide="ignore"):  # NaN = the tracker records nothing for that task (count 0)
+            rec["null_acc1"] = np.where(nul_n > 0, 100.0 * nul_ok / nul_n, np.nan)
+            rec["non_null_acc1"] = np.where(non_n > 0, 100.0 * non_ok / non_n, np.nan)
         rec["chain_accuracy"], rec["partial_chain_accuracy"] = np.array(chain / tot), np.array(partial / tot)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
         print(name, "acc1", rec["acc1"], "chain", rec["chain_accuracy"], "partial", rec["partial_chain_accuracy"])

@@ -45,6 +45,9 @@ def test_phase_accumulator_matches_reference_golden(name):
     assert m["chain_accuracy"] == pytest.approx(float(g["chain_accuracy"]), abs=1e-12)
     assert m["partial_chain_accuracy"] == pytest.approx(float(g["partial_chain_accuracy"]), abs=1e-12)
     assert m["samples"] == sum(CASES[name][0])
+    for f in ("null_acc1", "non_null_acc1"):  # the tracker's null / non-null split (restated inline in make_golden_metrics.py)
+        ref = {k: float(v) for k, v in zip(keys, g[f]) if not np.isnan(v)}
+        assert m[f] == pytest.approx(ref, abs=1e-9)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -69,7 +72,7 @@ def test_counters_and_ranks_bit_exact_vs_oracle(dtype, B, classes):
     ranks, _ = M.hier_metrics(cat, offs, tg, want_ranks=True)
     ref_r = np.stack([MO.target_rank(o, y) for o, y in zip(outs, tgts)])
     assert np.array_equal(ranks.cpu().numpy(), ref_r)
-    counters = torch.full((2 * len(classes) + 4,), 7, dtype=torch.int64, device=DEV)  # ADDED to, not overwritten
+    counters = torch.full((4 * len(classes) + 4,), 7, dtype=torch.int64, device=DEV)  # ADDED to, not overwritten
     M.hier_metrics(cat, offs, tg, counters=counters)
     assert np.array_equal(counters.cpu().numpy() - 7, MO.phase_counters(outs, tgts))
     # one-hot targets are arg-maxed by the host mirror

@@ -27,6 +27,7 @@ def test_finalize_reproduces_the_tracker_arithmetic(name):
     for f in ("chain_accuracy", "partial_chain_accuracy"):
         assert got[f] == pytest.approx(ref[f], abs=1e-12)
     assert got["acc1"] == pytest.approx(ref["acc1"]) and got["acc3"] == pytest.approx(ref["acc3"])
+    assert got["null_acc1"] == pytest.approx(ref["null_acc1"]) and got["non_null_acc1"] == pytest.approx(ref["non_null_acc1"])
     assert HierMetricsAccumulator._finalize([], keys, torch.device("cpu"), all_reduce=False)["samples"] == 0
 
 
@@ -71,3 +72,4 @@ def test_finalize_all_reduces_over_ranks():
         assert res[r]["chain_accuracy"] == pytest.approx(ref["chain_accuracy"], abs=1e-12)
         assert res[r]["partial_chain_accuracy"] == pytest.approx(ref["partial_chain_accuracy"], abs=1e-12)
         assert res[r]["acc1"] == pytest.approx(ref["acc1"]) and res[r]["acc3"] == pytest.approx(ref["acc3"])
+        assert res[r]["null_acc1"] == pytest.approx(ref["null_acc1"]) and res[r]["non_null_acc1"] == pytest.approx(ref["non_null_acc1"])

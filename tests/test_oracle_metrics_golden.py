@@ -29,6 +29,8 @@ def test_metrics_oracle_reproduces_reference_golden(name):
     np.testing.assert_allclose([m["acc3"][k] for k in keys], g["acc3"], rtol=0, atol=1e-9)
     assert m["chain_accuracy"] == pytest.approx(float(g["chain_accuracy"]), abs=1e-12)
     assert m["partial_chain_accuracy"] == pytest.approx(float(g["partial_chain_accuracy"]), abs=1e-12)
+    for f in ("null_acc1", "non_null_acc1"):
+        assert m[f] == pytest.approx({k: float(v) for k, v in zip(keys, g[f]) if not np.isnan(v)}, abs=1e-9)
 
 
 def test_rank_tie_rule_is_first_index():

@@ -63,7 +63,7 @@ offs = [0]
 for c in classes:
     offs.append(offs[-1] + c)
 tg = torch.stack([tgts[k] for k in keys])
-counters = torch.zeros(2 * len(keys) + 4, dtype=torch.int64, device=dev)
+counters = torch.zeros(4 * len(keys) + 4, dtype=torch.int64, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 M.hier_metrics(cat, offs, tg, counters=counters)
 e0.record()
