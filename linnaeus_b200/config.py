@@ -5,7 +5,7 @@ small part of its API (attribute access, ``get``, ``clone``, ``defrost`` /
 ``freeze``, ``merge_from_file`` / ``merge_from_other_cfg`` / ``merge_from_list``,
 ``load_cfg``, ``new_allowed``).  This class covers that surface so that
 
-* the YAML schema of ``/root/reference/configs/**`` loads unchanged, and
+* the YAML schema of the reference's ``configs/**`` loads unchanged, and
 * a real ``yacs.config.CfgNode`` passed in by ``linnaeus/main.py`` works too,
   because the model only ever uses ``.get`` / attribute access / ``hasattr``.
 
@@ -245,7 +245,7 @@ def get_default_config() -> CfgNode:
 # ---------------------------------------------------------------------------
 # Architecture presets.  Values are those of the reference's arch YAMLs
 # (configs/model/archs/mFormerV1/mFormerV1_{sm,md,lg,xl}.yaml), restated here
-# so benchmarks and tests do not need /root/reference at run time.
+# so benchmarks and tests do not need the reference tree at run time.
 # ---------------------------------------------------------------------------
 _ARCH_V1 = {
     #        convnext depths      dims                     rope depths  heads      drop_path
