@@ -50,7 +50,9 @@ def _worker(rank, world, port, overlap, q):
         ((dp(xs[2:]) - ys[2:]) ** 2).mean().mul(0.5).backward()
         dp.finish_gradients()
         out.append(g.g.clone())
-    q.put((rank, out, g.p.clone()))
+    # plain numpy payloads: torch tensors travel through a Queue as shared file descriptors, which the parent may try to fetch
+    # after this process has already exited
+    q.put((rank, [o.numpy().copy() for o in out], g.p.detach().numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,7 +72,7 @@ def _launch(overlap):
     try:
         for _ in range(2):
             r, out, params = q.get(timeout=180)
-            res[r] = (out, params)
+            res[r] = ([torch.from_numpy(o) for o in out], torch.from_numpy(params))
     except queue.Empty:
         res = None
     for p in procs:
