@@ -134,13 +134,18 @@ def backbone_parameters(model: nn.Module, exclude_patterns=("head", "meta_")) ->
 
 
 def task_gradient_norms(model, images, aux_info, targets: dict, criteria: dict, task_keys: list[str], backbone_params=None,
-                        zero_aux_info: bool = True, optimizer=None, dp=None) -> tuple[dict, dict]:
+                        zero_aux_info: bool = True, optimizer=None, dp=None, accum_steps: int = 1) -> tuple[dict, dict]:
     """-> (unweighted_losses {task: 0-dim}, grad_norms {task: 0-dim}), no host sync.
 
     Per task k (R/loss/gradient_weighting.py:478-760, one sub-batch): loss_k = sum of the criterion's per-sample losses over the
     non-null samples (label != 0, or one-hot[:, 0] <= 0.5) / max(#non-null, 1); norm_k = || d loss_k / d backbone ||_2.  The
     metadata input is zeroed when ``zero_aux_info`` (the reference's default).  ``optimizer`` (FlatAdamW) / ``dp`` (DataParallel)
-    are only used to zero the flat gradient buffer and to keep the measurement passes out of the gradient all-reduce."""
+    are only used to zero the flat gradient buffer and to keep the measurement passes out of the gradient all-reduce.
+
+    ``accum_steps`` > 1 (``GRADNORM_ACCUM_STEPS``, a memory device of the reference): the reference sums, over sub-batches of
+    B // accum_steps samples (the last one takes the remainder), the gradients of each sub-batch's own mean loss, and reports
+    total loss / total non-null count (:478-800).  By linearity that gradient is the gradient of sum_i loss_i * valid_i /
+    max(n_valid(sub-batch of i), 1), so it is measured here with the same single forward - no sub-batch passes."""
     import contextlib
 
     params = list(backbone_params) if backbone_params is not None else backbone_parameters(model)
@@ -167,8 +172,18 @@ def task_gradient_norms(model, images, aux_info, targets: dict, criteria: dict, 
             loss_vec = criteria[k](outputs[k], tgt)
             vf = valid.to(loss_vec.dtype)
             partial = (loss_vec * vf).sum() / vf.sum().clamp(min=1.0)
+            if accum_steps > 1:
+                B = vf.shape[0]
+                sb = B // accum_steps
+                w = torch.empty_like(vf)
+                for s_idx in range(accum_steps):
+                    lo, hi = s_idx * sb, ((s_idx + 1) * sb if s_idx < accum_steps - 1 else B)
+                    w[lo:hi] = vf[lo:hi] / vf[lo:hi].sum().clamp(min=1.0)
+                grad_loss = (loss_vec * w).sum()
+            else:
+                grad_loss = partial
             zero_grads()
-            partial.backward(retain_graph=i + 1 < len(task_keys))
+            grad_loss.backward(retain_graph=i + 1 < len(task_keys))
             grads = [p.grad for p in params if p.grad is not None]
             norms[k] = torch.stack(torch._foreach_norm(grads)).norm(2) if grads else torch.zeros((), device=images.device)
             losses[k] = partial.detach()
@@ -178,10 +193,10 @@ def task_gradient_norms(model, images, aux_info, targets: dict, criteria: dict, 
 
 
 def update_gradnorm_weights(gradnorm: GradNormModule, model, data_batch, criteria: dict, zero_aux_info: bool = True, optimizer=None, dp=None,
-                            backbone_params=None, return_metrics: bool = True) -> dict:
-    """The B200 counterpart of ``GradientWeighting.update_gradnorm_weights_reforward`` for one sub-batch: measure, then update.
+                            backbone_params=None, return_metrics: bool = True, accum_steps: int = 1) -> dict:
+    """The B200 counterpart of ``GradientWeighting.update_gradnorm_weights_reforward``: measure, then update.
     ``data_batch`` = (images, targets_dict, aux_info, ...)."""
     images, targets, aux = data_batch[0], data_batch[1], data_batch[2]
     losses, norms = task_gradient_norms(model, images, aux, targets, criteria, list(gradnorm.task_keys), backbone_params, zero_aux_info,
-                                        optimizer, dp)
+                                        optimizer, dp, accum_steps)
     return gradnorm.measure_and_update(losses, norms, return_metrics=return_metrics)

@@ -276,6 +276,21 @@ def test_gradnorm_task_gradient_norms_match_oracle_autograd(with_optimizer):
     ref.measure_and_update({k: torch.tensor(v) for k, v in ref_loss.items()}, {k: torch.tensor(v) for k, v in ref_norm.items()})
     torch.testing.assert_close(gn.task_weights.cpu(), ref.task_weights, rtol=2e-4, atol=1e-6)
     assert f"gradnorm/weight/{keys[0]}" in m
+    # GRADNORM_ACCUM_STEPS = 3: the reference sums the gradients of each sub-batch's own mean loss (4 samples -> sub-batches of
+    # 1, 1, 2) and reports total loss / total non-null count; here that is one forward with per-sample weights
+    B = x.shape[0]
+    logits = O.forward(leaves, a, x, torch.zeros_like(meta))
+    sb = B // 3
+    bounds = [(s * sb, (s + 1) * sb if s < 2 else B) for s in range(3)]
+    losses3, norms3 = G.task_gradient_norms(model, x.to(DEV), meta.to(DEV), tgd, crit, keys, optimizer=opt, accum_steps=3)
+    for k in keys:
+        lv = TF.cross_entropy(logits[k], tg[k], reduction="none")
+        valid = tg[k] != 0
+        tot = sum(lv[lo:hi][valid[lo:hi]].sum() / max(int(valid[lo:hi].sum()), 1) for lo, hi in bounds)
+        gs = torch.autograd.grad(tot, [leaves[n] for n in backbone], retain_graph=True, allow_unused=True)
+        rn = float(torch.sqrt(sum((g ** 2).sum() for g in gs if g is not None)))
+        assert float(norms3[k]) == pytest.approx(rn, rel=1e-4), (k, float(norms3[k]), rn)
+        assert float(losses3[k]) == pytest.approx(float(lv[valid].sum() / max(int(valid.sum()), 1)), rel=1e-4)
     # a normal training step still works afterwards (the graph of the measurement passes is gone, grads are clean)
     out, total = _loss(L, O, model, a, kind, x, meta, tg, cfg)
     total.backward()
