@@ -17,7 +17,6 @@ the keys the hot path reads are reproduced in :func:`get_default_config`),
 from __future__ import annotations
 
 import copy
-import os
 from ast import literal_eval
 from typing import Any
 

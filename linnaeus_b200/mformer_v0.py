@@ -30,7 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as TF
 
 from . import functional as F
-from ._lib import call, dt, ptr
+from ._lib import call, dt
 from .heads import configure_classification_heads
 from .mformer_v1 import LogitsDict, Mlp, _meta_head, _run_meta_head, trunc_normal_
 from .registry import register_model

@@ -11,7 +11,6 @@ The flat gradient buffers are also what ``linnaeus_b200.DataParallel`` all-reduc
 """
 from __future__ import annotations
 
-import math
 
 import torch
 
