@@ -186,11 +186,14 @@ class mFormerV0(nn.Module):
             if info["dim"] <= 0:
                 raise ValueError("metadata components with DIM 0 are not supported")
             setattr(self, f"meta_{name.lower()}_head_1", _meta_head(info["dim"], D3))
-            setattr(self, f"meta_{name.lower()}_head_2", _meta_head(info["dim"], D4))
         self.stage_3 = nn.ModuleList([
             RelativeMHSABlock(self.conv_out_channels[-1] if i == 0 else D3, D3, (hw3, hw3), self.attn_stride_seqs[0][i], self.num_heads_list[0],
                               self.mlp_ratio_list[0], self.extra_token_num) for i in range(self.attn_depths[0])])
         self.norm_1 = nn.LayerNorm(D3)
+        # registration order = the reference's (R/models/mFormerV0.py:225-320): stage-3 heads, stage_3, norm_1, stage-4 heads,
+        # stage_4 ... so state_dict() and named_parameters() enumerate identically (index-based optimizer state interchange)
+        for name, info in self.meta_components.items():
+            setattr(self, f"meta_{name.lower()}_head_2", _meta_head(info["dim"], D4))
         self.stage_4 = nn.ModuleList([
             RelativeMHSABlock(D3 if i == 0 else D4, D4, (hw4, hw4), self.attn_stride_seqs[1][i], self.num_heads_list[1], self.mlp_ratio_list[1],
                               self.extra_token_num) for i in range(self.attn_depths[1])])

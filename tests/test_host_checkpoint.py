@@ -51,3 +51,45 @@ def test_save_load_roundtrip_and_auto_resume(tmp_path):
     assert opt2.param_groups[0]["lr"] == 1e-3
     with pytest.raises(RuntimeError):
         C.load_checkpoint(p1, torch.nn.Linear(4, 3))
+
+
+@pytest.mark.skipif(not refload.reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("arch", ["v1", "v0"])
+def test_checkpoints_interchange_with_the_reference_model(arch, tmp_path):
+    """A checkpoint of the REFERENCE model (DDP-prefixed, reference dict layout) loads strictly into the B200 model and a
+    checkpoint written here loads strictly into the reference model: same keys, shapes and values both ways."""
+    import linnaeus_b200 as L
+
+    refload.import_reference()
+    from linnaeus.models import build_model as ref_build
+
+    if arch == "v1":
+        rcfg, nc = refload.reference_config("sm", 64, dims=(32, 64, 128, 256), heads=(2, 4), rope_depths=(1, 1), conv_depths=(1, 1, 1, 1))
+        cfg, _ = L.make_synthetic_config("sm", 64, dims=(32, 64, 128, 256), heads=(2, 4), rope_depths=(1, 1), conv_depths=(1, 1, 1, 1))
+    else:
+        kw = dict(conv_embed=(16, 32), conv_out=(32, 64), conv_depths=(1, 2), conv_strides=((2,), (1, 1)), attn_dims=(64, 128), attn_depths=(2, 1),
+                  heads=(2, 4))
+        rcfg, nc = refload.reference_config_v0(img_size=64, **kw)
+        cfg, _ = L.make_synthetic_config_v0("sm", 64, **kw)
+    torch.manual_seed(1)
+    ref = ref_build(rcfg, num_classes=nc, taxonomy_tree=None)
+    ours = L.build_model(cfg, nc)
+    # reference -> here (as DDP would have saved it)
+    torch.save({"model": {f"module.{k}": v for k, v in ref.state_dict().items()}, "optimizer": None, "lr_scheduler": None, "epoch": 3,
+                "config": None, "iteration": 11}, tmp_path / "ref.pth")
+    rest = C.load_checkpoint(str(tmp_path / "ref.pth"), ours, strict=True)
+    assert rest["epoch"] == 3 and rest["iteration"] == 11
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+    # here -> reference
+    with torch.no_grad():
+        for p in ours.parameters():
+            p.add_(0.25)
+    path = C.save_checkpoint(str(tmp_path), ours, None, epoch=4)
+    ck = torch.load(path, weights_only=False)
+    missing, unexpected = ref.load_state_dict(ck["model"], strict=True)
+    assert not missing and not unexpected
+    for k, v in ours.state_dict().items():
+        assert torch.equal(ref.state_dict()[k], v), k
