@@ -149,3 +149,41 @@ class TrainStep:
             self.opt.zero_grad()
         self.loss = self._static_loss
         return self._static_loss
+
+
+@torch.no_grad()
+def validate_one_pass(config, model, data_loader, criteria: dict, task_weighting, mask_meta: bool = False, all_reduce: bool | None = None) -> dict:
+    """One validation pass right after the hot path (R/validation.py:49-340): ``model.eval()``, forward, the hierarchical loss with
+    null masking disabled (``is_validation=True``), and the tracker's per-batch accumulation - without a single host sync per
+    batch: the loss sum stays on the device and the metrics go through ``HierMetricsAccumulator`` (one kernel per batch); the only
+    device->host reads happen once, after the loop.  ``mask_meta`` zeroes the metadata (the reference's "val_mask_meta" phase).
+    ``data_loader`` yields ``(images, targets_dict, aux_info, ...)``.  Returns ``{"loss": avg loss per batch, "batches": n,
+    **HierMetricsAccumulator.compute()}``; under ``torch.distributed`` the sums are reduced over the ranks like the tracker's."""
+    from .metrics import HierMetricsAccumulator
+
+    was_training = model.training
+    model.eval()
+    acc = HierMetricsAccumulator()
+    loss_sum, n_batches, dev = None, 0, None
+    for batch in data_loader:
+        images, targets, aux = batch[0], batch[1], batch[2]
+        dev = images.device
+        if mask_meta and aux is not None:
+            aux = torch.zeros_like(aux)
+        outputs = model(images, aux)
+        total, _, _ = LL.weighted_hierarchical_loss(outputs, targets, criteria, task_weighting, None, 0, is_validation=True, config=config)
+        loss_sum = total.detach().float() if loss_sum is None else loss_sum + total.detach().float()
+        acc.update(outputs, targets)
+        n_batches += 1
+    model.train(was_training)
+    out = acc.compute(all_reduce=all_reduce)
+    local = torch.stack([loss_sum if loss_sum is not None else torch.zeros((), device=dev or "cpu"),
+                         torch.tensor(float(n_batches), device=dev or "cpu")])
+    import torch.distributed as dist
+
+    if all_reduce or (all_reduce is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+    s, n = local.tolist()
+    out["loss"] = s / n if n > 0 else 0.0
+    out["batches"] = int(n)
+    return out

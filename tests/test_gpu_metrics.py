@@ -135,3 +135,44 @@ def test_cpu_tensors_are_rejected():
     M = _M()
     with pytest.raises(RuntimeError):
         M.accuracy(torch.randn(4, 5), torch.zeros(4, dtype=torch.int64))
+
+
+def test_validate_one_pass_matches_per_batch_evaluation():
+    """engine.validate_one_pass (no per-batch host sync) against the same loop done by hand with the reference-named metric functions
+    and the loss called per batch; mask_meta changes the logits, so it must change the loss."""
+    import linnaeus_b200 as L
+    import linnaeus_b200.loss as LL
+    from linnaeus_b200.config import make_synthetic_config
+    from linnaeus_b200.engine import validate_one_pass
+
+    M = _M()
+    torch.manual_seed(0)
+    cfg, nc = make_synthetic_config("sm", 64, dims=(32, 64, 128, 256), heads=(2, 4), rope_depths=(1, 1), conv_depths=(1, 1, 1, 1), n_tasks=3)
+    model = L.build_model(cfg, nc).to(DEV).train()
+    keys = list(nc.keys())
+    crit = {k: LL.CrossEntropyLoss() for k in keys}
+    tw = LL.StaticTaskWeighting(keys)
+    batches = []
+    for b in (5, 8, 3):
+        tg = {k: torch.randint(0, nc[k], (b,), device=DEV) for k in keys}
+        batches.append((torch.randn(b, 3, 64, 64, device=DEV), tg, torch.randn(b, 15, device=DEV)))
+    res = validate_one_pass(cfg, model, batches, crit, tw)
+    assert model.training  # restored
+    model.eval()
+    losses, chain, part, tot, c1 = [], 0.0, 0.0, 0, {k: 0 for k in keys}
+    with torch.no_grad():
+        for x, tg, aux in batches:
+            out = model(x, aux)
+            losses.append(float(LL.weighted_hierarchical_loss(out, tg, crit, tw, None, 0, is_validation=True, config=cfg)[0]))
+            ol, tl = [out[k] for k in keys], [tg[k] for k in keys]
+            chain += M.compute_chain_accuracy_vectorized(ol, tl) * x.shape[0]
+            part += M.compute_partial_chain_accuracy_vectorized(ol, tl) * x.shape[0]
+            tot += x.shape[0]
+            for k in keys:
+                c1[k] += int((out[k].float().argmax(1) == tg[k]).sum())
+    assert res["batches"] == 3 and res["samples"] == tot
+    assert res["loss"] == pytest.approx(sum(losses) / 3, rel=1e-5)
+    assert res["chain_accuracy"] == pytest.approx(chain / tot, abs=1e-12) and res["partial_chain_accuracy"] == pytest.approx(part / tot, abs=1e-12)
+    assert res["acc1"] == pytest.approx({k: 100.0 * c1[k] / tot for k in keys})
+    masked = validate_one_pass(cfg, model, batches, crit, tw, mask_meta=True)
+    assert masked["loss"] != res["loss"] and masked["samples"] == tot
