@@ -30,7 +30,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-__all__ = ["GradNormModule", "backbone_parameters", "task_gradient_norms", "update_gradnorm_weights"]
+__all__ = ["GradNormModule", "GradientWeighting", "backbone_parameters", "task_gradient_norms", "update_gradnorm_weights"]
 
 
 def _allreduce_mean(value: torch.Tensor) -> torch.Tensor:
@@ -200,3 +200,97 @@ def update_gradnorm_weights(gradnorm: GradNormModule, model, data_batch, criteri
     losses, norms = task_gradient_norms(model, images, aux, targets, criteria, list(gradnorm.task_keys), backbone_params, zero_aux_info,
                                         optimizer, dp, accum_steps)
     return gradnorm.measure_and_update(losses, norms, return_metrics=return_metrics)
+
+
+class GradientWeighting(nn.Module):
+    """Task weighting for the hierarchical loss, static or GradNorm (R/loss/gradient_weighting.py:178-365 plus the driver :367-923).
+
+    Same constructor arguments and attributes as the reference class (``task_keys``, ``task_weights``, ``class_weights``,
+    ``gradnorm``, ``update_interval``, ``zero_aux_info``, ``backbone_params``, ``model``), so
+    ``linnaeus_b200.loss.weighted_hierarchical_loss(..., grad_weighting, ...)`` - which reads ``gradnorm.task_weights`` /
+    ``task_weights`` / ``class_weights`` on the device, without the reference's per-sample ``.item()`` class-weight loop - and
+    ``train.py``'s ``grad_weighting.update_gradnorm_weights_reforward(batch, criteria, ...)`` call work unchanged.
+    ``forward`` is the reference's per-task reduction (mean over ``num_valid`` with optional class weights, times the task weight)
+    with the class weights gathered by one indexing op instead of a Python loop."""
+
+    def __init__(self, task_keys: list[str], config, task_weighting_type: str = "static", init_weights=None, class_weights=None,
+                 use_subset_weights: bool = False, alpha: float = 1.5, label_densities=None, num_classes=None,
+                 init_strategy: str = "inverse_density", update_interval: int = 100, exclude_patterns=None, zero_aux_info: bool = True):
+        super().__init__()
+        self.task_keys = task_keys
+        self.config = config
+        self.task_weighting_type = task_weighting_type
+        try:
+            self.zero_aux_info = getattr(config.LOSS.GRAD_WEIGHTING.TASK, "ZERO_AUX_INFO", zero_aux_info)
+        except AttributeError:
+            self.zero_aux_info = zero_aux_info
+        if isinstance(init_weights, dict):
+            init_weights = [init_weights.get(k, 1.0) for k in task_keys]
+        init_weights = init_weights or [1.0] * len(task_keys)
+        self.task_weights = torch.tensor(init_weights, dtype=torch.float32)
+        if task_weighting_type == "gradnorm":
+            self.gradnorm = GradNormModule(task_keys=task_keys, alpha=alpha, init_weights=torch.tensor(init_weights, dtype=torch.float32),
+                                           label_densities=label_densities, num_classes=num_classes, init_strategy=init_strategy, config=config)
+            self.update_interval = update_interval
+            self.exclude_patterns = exclude_patterns or ["head", "meta_"]
+        else:
+            self.gradnorm = None
+            self.update_interval = 0
+            self.exclude_patterns = []
+        self.backbone_params = None
+        self.model = None
+        self.class_weights = class_weights
+        self.use_subset_weights = use_subset_weights
+
+    def set_model(self, model: nn.Module) -> None:
+        """Identify the shared backbone (R/loss/gradient_weighting.py:265-299; name patterns, the default EXCLUDE_CONFIG)."""
+        if self.task_weighting_type == "gradnorm":
+            self.model = model
+            self.backbone_params = backbone_parameters(model, tuple(self.exclude_patterns))
+
+    def _normalize_weights(self, weights: torch.Tensor) -> torch.Tensor:
+        return weights  # identity in the reference as well (:360-365)
+
+    def forward(self, per_task_losses: dict, targets: dict, subset_ids=None, mixed_subset_ids=None, num_valid_samples_per_task=None):
+        """-> ({task: weighted mean loss}, {task: weight}) (R/loss/gradient_weighting.py:301-358)."""
+        first = next(iter(per_task_losses.values()))
+        device, dtype = first.device, first.dtype
+        src = self.gradnorm.task_weights if self.gradnorm is not None else self._normalize_weights(self.task_weights)
+        norm_w = src.to(device=device, dtype=dtype)
+        weighted = {}
+        for i, k in enumerate(self.task_keys):
+            loss_vec = per_task_losses[k]
+            num_valid = loss_vec.size(0) if num_valid_samples_per_task is None else num_valid_samples_per_task.get(k, loss_vec.size(0))
+            if self.class_weights and k in self.class_weights:
+                cw = self.class_weights[k]
+                tgt = targets[k]
+                C = tgt.size(1) if tgt.dim() > 1 else (int(max(cw.keys(), default=0)) + 1)
+                with torch.no_grad():
+                    vec = torch.ones(max(C, 1), dtype=dtype)
+                    for idx, w in cw.items():
+                        if 0 <= int(idx) < vec.numel():
+                            vec[int(idx)] = float(w)
+                    vec = vec.to(device)
+                    if tgt.dim() == 1:
+                        # labels beyond the largest weighted class keep weight 1.0 like dict.get(label, 1.0)
+                        inside = tgt < vec.numel()
+                        sample_wt = torch.where(inside, vec[tgt.clamp(max=vec.numel() - 1)], torch.ones((), dtype=dtype, device=device))
+                    else:
+                        sample_wt = (tgt.to(dtype) * vec.unsqueeze(0)).sum(dim=1)
+                loss_vec = loss_vec * sample_wt
+            weighted[k] = (loss_vec.sum() / max(float(num_valid), 1e-6)) * norm_w[i]
+        return weighted, dict(zip(self.task_keys, norm_w.tolist()))
+
+    def update_gradnorm_weights_reforward(self, data_batch, criteria: dict, amp_enabled: bool = True, ops_schedule=None, current_step=None,
+                                          optimizer=None, dp=None, return_metrics: bool = True) -> dict:
+        """The reference's GradNorm update entry point (:367-923), here one forward + K backward passes (``update_gradnorm_weights``).
+        ``amp_enabled`` / ``ops_schedule`` / ``current_step`` are accepted for call compatibility (the model's compute dtype decides
+        the precision).  ``GRADNORM_ACCUM_STEPS`` is read from the config when present."""
+        if self.task_weighting_type != "gradnorm" or self.gradnorm is None or self.model is None or not self.backbone_params:
+            return {}
+        try:
+            accum = int(self.config.LOSS.GRAD_WEIGHTING.TASK.GRADNORM_ACCUM_STEPS)
+        except (AttributeError, KeyError, TypeError):
+            accum = 1
+        return update_gradnorm_weights(self.gradnorm, self.model, data_batch, criteria, zero_aux_info=bool(self.zero_aux_info), optimizer=optimizer,
+                                       dp=dp, backbone_params=self.backbone_params, return_metrics=return_metrics, accum_steps=max(accum, 1))

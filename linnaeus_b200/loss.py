@@ -107,6 +107,45 @@ def _class_weight_vec(cw: dict, C: int, device) -> torch.Tensor:
     return v.to(device)
 
 
+def _task_weight_vector(task_weighting, keys: list[str], dev) -> torch.Tensor | None:
+    """float32 [K] task weights on ``dev`` in the order of ``keys`` (gradient_weighting.py:317-323: the GradNorm buffer when GradNorm
+    is active, else the static vector).  Static weights are uploaded once and cached on the weighting object (keeps the step
+    CUDA-graph capturable); GradNorm weights are read from the live buffer every call, on the device, with no host round trip."""
+    gn = getattr(task_weighting, "gradnorm", None)
+    w_src = gn.task_weights if gn is not None else getattr(task_weighting, "task_weights", None)
+    if w_src is None:
+        return None
+    order = list(getattr(task_weighting, "task_keys", keys))
+    idx = [order.index(k) for k in keys]
+    ck = (str(dev), tuple(keys))
+    if gn is not None:
+        w = w_src.detach().to(device=dev, dtype=torch.float32)
+        if idx == list(range(len(order))):
+            return w
+        cache = getattr(task_weighting, "_lnx_idx_cache", None)
+        if cache is None:
+            cache = {}
+            try:
+                task_weighting._lnx_idx_cache = cache
+            except Exception:
+                pass
+        if ck not in cache:
+            cache[ck] = torch.tensor(idx, dtype=torch.int64, device=dev)
+        return w[cache[ck]]
+    cache = getattr(task_weighting, "_lnx_tw_cache", None)
+    if cache is not None and ck in cache:
+        return cache[ck]
+    w_cpu = w_src.detach().float().cpu()
+    tw = torch.tensor([float(w_cpu[i]) for i in idx], dtype=torch.float32, device=dev)
+    try:
+        if cache is None:
+            task_weighting._lnx_tw_cache = {}
+        task_weighting._lnx_tw_cache[ck] = tw
+    except Exception:
+        pass
+    return tw
+
+
 def weighted_hierarchical_loss(
     outputs: dict[str, torch.Tensor],
     targets: dict[str, torch.Tensor],
@@ -176,25 +215,7 @@ def weighted_hierarchical_loss(
                 mult[i] = _class_weight_vec(cw[k], C, dev)[tg[i]].pow(times)
         keep = mult if keep is None else keep * mult
 
-    tw = None
-    gn = getattr(task_weighting, "gradnorm", None)
-    w_src = gn.task_weights if gn is not None else getattr(task_weighting, "task_weights", None)
-    if w_src is not None:
-        cache = getattr(task_weighting, "_lnx_tw_cache", None) if gn is None else None
-        ck = (str(dev), tuple(keys))
-        if cache is not None and ck in cache:
-            tw = cache[ck]
-        else:
-            order = list(getattr(task_weighting, "task_keys", keys))
-            w_cpu = w_src.detach().float().cpu()
-            tw = torch.tensor([float(w_cpu[order.index(k)]) for k in keys], dtype=torch.float32, device=dev)
-            if gn is None:  # static weights: upload once (keeps the step CUDA-graph capturable)
-                try:
-                    if cache is None:
-                        task_weighting._lnx_tw_cache = {}
-                    task_weighting._lnx_tw_cache[ck] = tw
-                except Exception:
-                    pass
+    tw = _task_weight_vector(task_weighting, keys, dev)
 
     soft = None
     if kind == LOSS_TAXONOMY:
