@@ -104,6 +104,16 @@ int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias,
 int lnx_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx, float* dw, float* db, int64_t M, int N, int K, int dtype,
               lnx_stream_t s);
 
+/* ---- fused ConvNeXt pointwise pair ---------------------------------------- */
+/* y[M,C] = residual + row_scale[m / rows_per_group] * gamma * (gelu(x W1^T + b1) W2^T + b2), all activations bf16.
+ * One tcgen05 kernel: the [M, H = 4C] hidden tensor stays in TMEM (the GELU output is written back into the
+ * accumulator's columns and read by the second MMA as its A operand).  gamma, row_scale, residual, b1, b2 may be
+ * NULL.  C in {96, 192}; anything else returns LNX_ERR_UNSUPPORTED (the caller then runs two lnx_gemm calls).
+ * Replaces pwconv1 -> GELU -> pwconv2 -> gamma -> DropPath -> + input, R/models/blocks/convnext.py:79-86. */
+int lnx_mlp_fused_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* gamma,
+                      const float* row_scale, int rows_per_group, const void* residual, void* y, int64_t M, int C, int H,
+                      lnx_stream_t s);
+
 /* acc[m,n] = sum_k A(m,k) * B(n,k)
  *   a_trans = 0: A stored [M,K] (row pitch lda); 1: stored [K,M]
  *   b_trans = 0: B stored [N,K] (row pitch ldb); 1: stored [K,N]

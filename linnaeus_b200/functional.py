@@ -196,6 +196,28 @@ def linear(x, weight, bias=None, weight_c=None, act=None, residual=None, x_ld=No
     return _Linear.apply(x, weight, bias, weight_c, _ACT[act], residual, x_ld, out_dtype, row_scale, rows_per_group, torch.is_grad_enabled())
 
 
+# --------------------------------------------------------------------------- fused ConvNeXt pointwise pair
+FUSED_MLP = True  # tests flip this to compare against the two-GEMM path
+_FUSED_C = (96, 192)
+
+
+def fused_mlp_ok(x2: torch.Tensor, K: int, Hd: int, N: int, act) -> bool:
+    """The single-kernel pointwise pair (lnx_mlp_fused_*) covers bf16, C in {96, 192}, hidden = 4 C, GELU."""
+    return (FUSED_MLP and not FORCE_SIMT and x2.dtype == torch.bfloat16 and act == ACT_GELU and K == N and K in _FUSED_C
+            and Hd == 4 * K)
+
+
+def mlp_fused_fwd(x2, w1c, b1, w2c, b2, gamma=None, row_scale=None, rows_per_group=0, residual=None, out=None):
+    """y = residual + row_scale * gamma * (gelu(x W1^T + b1) W2^T + b2): one tcgen05 kernel, hidden tile kept in TMEM."""
+    M, C = x2.shape
+    Hd = w1c.shape[0]
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.bfloat16, device=x2.device)
+    call("lnx_mlp_fused_fwd", x2.data_ptr(), w1c.data_ptr(), ptr(b1), w2c.data_ptr(), ptr(b2), ptr(gamma), ptr(row_scale),
+         int(rows_per_group), ptr(residual), out.data_ptr(), M, C, Hd)
+    return out
+
+
 # --------------------------------------------------------------------------- two-layer MLP
 class _Mlp2(torch.autograd.Function):
     """y = [residual +] [col_scale *] (act(x W1^T + b1) W2^T + b2).

@@ -1,0 +1,116 @@
+"""Fused ConvNeXt pointwise pair: parity against fp32 torch on the same bf16 inputs, then timing at the bench shapes
+next to the two-GEMM path.  python tools/prof_mlp_fused.py [--no-time]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as TF
+
+import linnaeus_b200.functional as F
+
+DEV = "cuda"
+
+
+def ref(x, w1, b1, w2, b2, gamma, rs, rpg, res):
+    h = TF.gelu(x.float() @ w1.float().t() + (b1 if b1 is not None else 0.0)).to(torch.bfloat16).float()
+    y = h @ w2.float().t() + (b2 if b2 is not None else 0.0)
+    if gamma is not None:
+        y = y * gamma
+    if rs is not None:
+        y = y * rs.repeat_interleave(rpg)[: y.shape[0], None]
+    if res is not None:
+        y = y + res.float()
+    return y
+
+
+def make(M, C, seed=0, gamma_scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    H = 4 * C
+    x = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(H, C, device=DEV, generator=g) * C ** -0.5).to(torch.bfloat16)
+    w2 = (torch.randn(C, H, device=DEV, generator=g) * H ** -0.5).to(torch.bfloat16)
+    b1 = torch.randn(H, device=DEV, generator=g) * 0.5
+    b2 = torch.randn(C, device=DEV, generator=g) * 0.5
+    gamma = (torch.rand(C, device=DEV, generator=g) + 0.5) * gamma_scale
+    res = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    return x, w1, b1, w2, b2, gamma, res
+
+
+def check(M, C, use_gamma=True, use_res=True, use_rs=False, use_bias=True):
+    x, w1, b1, w2, b2, gamma, res = make(M, C)
+    rpg = 49
+    rs = None
+    if use_rs:
+        n = (M + rpg - 1) // rpg
+        rs = torch.floor(0.8 + torch.rand(n, device=DEV)) / 0.8
+    args = (x, w1, b1 if use_bias else None, w2, b2 if use_bias else None, gamma if use_gamma else None, rs, rpg, res if use_res else None)
+    y = F.mlp_fused_fwd(x, w1, args[2], w2, args[4], gamma=args[5], row_scale=rs, rows_per_group=rpg if use_rs else 0, residual=args[8])
+    torch.cuda.synchronize()
+    r = ref(*args)
+    err = float((y.float() - r).abs().max() / r.abs().max())
+    print(f"M={M:7d} C={C:3d} gamma={int(use_gamma)} res={int(use_res)} rs={int(use_rs)} bias={int(use_bias)}  rel err {err:.3e}", flush=True)
+    return err
+
+
+def timeit(fn, iters=20, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def bench_only(C, M, iters=5):
+    x, w1, b1, w2, b2, gamma, res = make(M, C)
+    out = torch.empty_like(x)
+    for _ in range(iters):
+        F.mlp_fused_fwd(x, w1, b1, w2, b2, gamma=gamma, residual=res, out=out)
+    torch.cuda.synchronize()
+
+
+def main():
+    if "--bench-only" in sys.argv:
+        C = int(sys.argv[sys.argv.index("--bench-only") + 1])
+        bench_only(C, 802816 if C == 96 else 200704)
+        return
+    worst = 0.0
+    for C in (96, 192):
+        for M in (128, 300, 4096 + 17, 50000):
+            worst = max(worst, check(M, C))
+        worst = max(worst, check(1000, C, use_gamma=False, use_res=False, use_bias=False))
+        worst = max(worst, check(3000, C, use_rs=True))
+    print("worst rel err", worst)
+    if "--no-time" in sys.argv:
+        return
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for C, M in ((96, 802816), (192, 200704)):
+        x, w1, b1, w2, b2, gamma, res = make(M, C)
+        worst = max(worst, check(M, C))
+        out = torch.empty_like(x)
+        t_f = timeit(lambda: F.mlp_fused_fwd(x, w1, b1, w2, b2, gamma=gamma, residual=res, out=out), flush=flush)
+
+        def two():
+            h = F.gemm(x, w1, M, 4 * C, C, bias=b1, act=F.ACT_GELU)
+            F.gemm(h, w2, M, C, 4 * C, bias=b2, residual=res, col_scale=gamma, out=out)
+
+        t_2 = timeit(two, flush=flush)
+        bytes_alg = 3 * M * C * 2
+        flops = 4.0 * M * C * 4 * C
+        print(f"C={C} M={M}: fused {t_f:.4f} ms ({bytes_alg / t_f / 1e6:.0f} GB/s algorithmic, {flops / t_f / 1e9:.0f} TFLOP/s) | two GEMMs {t_2:.4f} ms",
+              flush=True)
+    print("worst rel err (incl. bench shapes)", worst)
+
+
+if __name__ == "__main__":
+    main()
