@@ -113,6 +113,13 @@ int lnx_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx, float* dw
 int lnx_mlp_fused_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* gamma,
                       const float* row_scale, int rows_per_group, const void* residual, void* y, int64_t M, int C, int H,
                       lnx_stream_t s);
+/* Data path of its backward, with the pre-activation recomputed from x (the forward saves only its input):
+ *   h[M,H] = gelu(x W1^T + b1),  dpre[M,H] = (dy W2e) * gelu'(x W1^T + b1),  dx[M,C] = dpre W1,
+ * W2e = W2 * gamma[:, None] folded by the caller; dy already carries the DropPath row scale.  h and dpre feed the two
+ * weight-gradient GEMMs (lnx_wgrad).  C = 96 only (weights resident in shared memory); else LNX_ERR_UNSUPPORTED.
+ * Replaces autograd through R/models/blocks/convnext.py:79-86. */
+int lnx_mlp_fused_bwd(const void* x, const void* dy, const void* w1, const float* b1, const void* w2e, void* h, void* dpre, void* dx,
+                      int64_t M, int C, int H, lnx_stream_t s);
 
 /* acc[m,n] = sum_k A(m,k) * B(n,k)
  *   a_trans = 0: A stored [M,K] (row pitch lda); 1: stored [K,M]

@@ -41,6 +41,7 @@ SIGNATURES = {
     "lnx_gemm": [I, P, L, I, P, L, I, P, I, I, I, I, P, I, P, P, P, P, P, I, P, I, I, P],
     "lnx_wgrad": [P, L, P, L, P, P, L, I, I, I, P],
     "lnx_mlp_fused_fwd": [P, P, P, P, P, P, P, I, P, P, L, I, I, P],
+    "lnx_mlp_fused_bwd": [P, P, P, P, P, P, P, P, L, I, I, P],
     "lnx_im2col3x3": [P, I, P, I, I, I, I, I, I, I, I, I, P],
     "lnx_conv3x3_s1": [P, P, P, P, I, I, I, I, I, I, I, P],
     "lnx_maxpool3s2": [P, P, I, I, I, I, I, P],

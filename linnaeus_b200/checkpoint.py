@@ -48,7 +48,9 @@ def load_checkpoint(path: str, model, optimizer=None, lr_scheduler=None, strict:
     Returns the remaining entries (``epoch``, ``iteration``, ``config``, ...)."""
     ckpt = torch.load(path, map_location=map_location, weights_only=False)
     sd = ckpt["model"] if "model" in ckpt else ckpt
-    is_ddp = isinstance(model, torch.nn.parallel.DistributedDataParallel)
+    # like the reference (utils/checkpoint.py:798-830) the target model's own keys decide: torch's DDP and this package's
+    # DataParallel wrapper both expose ``module.``-prefixed names
+    is_ddp = any(k.startswith("module.") for k in model.state_dict())
     has_prefix = any(k.startswith("module.") for k in sd)
     model.load_state_dict(clean_state_dict_keys(sd, is_ddp, has_prefix), strict=strict)
     if optimizer is not None and ckpt.get("optimizer") is not None:

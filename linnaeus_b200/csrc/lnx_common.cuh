@@ -198,6 +198,29 @@ __device__ __forceinline__ void gelu_both_tanh3_x2(float2 x, float2& gl, float2&
   dg = __ffma2_rn(hn, sm1, __ffma2_rn(t, f2(0.5f), f2(0.5f)));
 }
 
+// Leanest erf-GELU for the fused pointwise-pair kernels, where the GELU warps are the critical resource: cubic argument
+// x (q0 + q1 x^2) (monotone, so no clamp; max |GELU error| 2.7e-4 before the bf16 rounding of the hidden tile, rms error
+// after rounding 1.703e-3 against 1.694e-3 for exact erf-GELU) and one MUFU.TANH per element.  Measured on B200:
+// MUFU.TANH issues at HALF the MUFU rate (8 / clk / SM), which is what bounds these kernels (2048 cycles per 128 x 128 chunk);
+// tanh.approx.f16x2 compiles to two MUFU.TANH.F16, so packing buys nothing.  gelu2q returns 2 gelu(x): the caller folds the
+// 0.5 into the next scale.  gelu2q_both also returns the derivative of the same approximation (backward recompute).
+constexpr float kGeluQ0 = 0.80015625f, kGeluQ1 = 0.034701171875f;
+__device__ __forceinline__ float2 gelu2q_x2(float2 x) {  // 2 gelu(x)
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 u = __fmul2_rn(x, __ffma2_rn(x2, f2(kGeluQ1), f2(kGeluQ0)));
+  return __ffma2_rn(x, make_float2(tanh_approx(u.x), tanh_approx(u.y)), x);
+}
+__device__ __forceinline__ void gelu2q_both_x2(float2 x, float2& g2, float2& dg) {  // 2 gelu(x) and gelu'(x)
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 u = __fmul2_rn(x, __ffma2_rn(x2, f2(kGeluQ1), f2(kGeluQ0)));
+  const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  g2 = __ffma2_rn(x, t, x);
+  // g' = 0.5 (1 + t) + 0.5 x (1 - t^2) (q0 + 3 q1 x^2)
+  const float2 xd = __fmul2_rn(x, __ffma2_rn(x2, f2(1.5f * kGeluQ1), f2(0.5f * kGeluQ0)));
+  const float2 omt2 = __ffma2_rn(make_float2(-t.x, -t.y), t, f2(1.0f));
+  dg = __ffma2_rn(xd, omt2, __ffma2_rn(t, f2(0.5f), f2(0.5f)));
+}
+
 // swish / SiLU = x sigmoid(x) = h (1 + tanh h), h = x / 2: one MUFU.TANH (bf16 tensor-core epilogues)
 __device__ __forceinline__ float swish_fast(float x) {
   const float h = 0.5f * x;

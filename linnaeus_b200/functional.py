@@ -218,6 +218,18 @@ def mlp_fused_fwd(x2, w1c, b1, w2c, b2, gamma=None, row_scale=None, rows_per_gro
     return out
 
 
+def mlp_fused_bwd(x2, dy2, w1c, b1, w2e):
+    """-> (h, dpre, dx): recomputes the pre-activation from x, one kernel (see lnx_mlp_fused_bwd)."""
+    M, C = x2.shape
+    Hd = w1c.shape[0]
+    h = torch.empty((M, Hd), dtype=torch.bfloat16, device=x2.device)
+    dpre = torch.empty((M, Hd), dtype=torch.bfloat16, device=x2.device)
+    dx = torch.empty((M, C), dtype=torch.bfloat16, device=x2.device)
+    call("lnx_mlp_fused_bwd", x2.data_ptr(), dy2.data_ptr(), w1c.data_ptr(), ptr(b1), w2e.data_ptr(), h.data_ptr(), dpre.data_ptr(),
+         dx.data_ptr(), M, C, Hd)
+    return h, dpre, dx
+
+
 # --------------------------------------------------------------------------- two-layer MLP
 class _Mlp2(torch.autograd.Function):
     """y = [residual +] [col_scale *] (act(x W1^T + b1) W2^T + b2).

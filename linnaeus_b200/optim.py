@@ -110,9 +110,16 @@ class FlatAdamW(torch.optim.Optimizer):
     # checkpoint interchange (R/utils/checkpoint.py:956-1200 saves ``optimizer.state_dict()`` of a torch.optim.AdamW, :738-953
     # loads it back): the state dict has torch.optim.AdamW's shape - per parameter index ``step`` / ``exp_avg`` / ``exp_avg_sq``
     # in param_groups order - so a reference checkpoint resumes here and one written here resumes in the reference.
+    def step_count(self) -> int:
+        """Optimizer steps taken so far.  The device counter is the source of truth: CUDA-graph replays advance it without
+        running ``step()`` on the host (one device->host read; call it at checkpoint time, not per step)."""
+        self._step = int(round(float(self._step_dev.item())))
+        return self._step
+
     def state_dict(self):
         sd = super().state_dict()
         state = {}
+        self.step_count()
         if self._step > 0:
             idx = 0
             for g, f in zip(self.param_groups, self.flat):
@@ -159,6 +166,8 @@ class FlatAdamW(torch.optim.Optimizer):
                 raise ValueError(f"FlatAdamW keeps one step count for all parameters; the state dict has {sorted(steps)}")
             self._step = steps.pop() if steps else 0
         self._step_dev.fill_(float(self._step))
+        if self._lr_dev is not None:  # a captured graph reads the learning rate from device memory
+            self.set_device_lr(self.param_groups[0]["lr"])
 
 
 def build_optimizer(config, model) -> FlatAdamW:

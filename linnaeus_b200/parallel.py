@@ -10,7 +10,9 @@ reverse of the order in which backward produces them.  The buffer is cut into bu
 a post-accumulate hook on every parameter counts its bucket down, and when the last
 gradient of a bucket has landed the bucket's slice is all-reduced asynchronously
 (NCCL over NVLink/NVSwitch; the collective runs on NCCL's stream, overlapping the rest
-of backward).  The 1/world factor is folded into the optimizer kernel
+of backward).  ``TrainStep.capture`` records these collectives INSIDE the step's CUDA graph
+(NCCL is capturable), so the benchmarked graph path overlaps them exactly like the eager one.
+With ``average=False`` the 1/world factor is folded into the optimizer kernel
 (``FlatAdamW.grad_scale``) instead of a separate pass over the gradients.
 """
 from __future__ import annotations
@@ -23,12 +25,13 @@ from .flat import FlatGroup, weights_changed
 
 
 class _Bucket:
-    __slots__ = ("group", "lo", "hi", "n_params", "pending", "work")
+    __slots__ = ("group", "lo", "hi", "n_params", "pending", "work", "streams")
 
     def __init__(self, group, lo, hi, n_params):
         self.group, self.lo, self.hi, self.n_params = group, lo, hi, n_params
         self.pending = n_params
         self.work = None
+        self.streams = {}  # CUDA streams that produced gradients of this bucket (the metadata branch runs on a side stream)
 
 
 def plan_buckets(groups: list[FlatGroup], bucket_bytes: int) -> tuple[list[_Bucket], dict[int, int]]:
@@ -96,12 +99,25 @@ class DataParallel(nn.Module):
 
     def _launch(self, b: _Bucket) -> None:
         buf = self.groups[b.group].g[b.lo:b.hi]
+        if buf.is_cuda and b.streams:
+            # NCCL orders the collective after the CURRENT stream only: join every other stream that wrote gradients of this
+            # bucket (under CUDA-graph capture the event pair becomes a graph edge)
+            cur = torch.cuda.current_stream()
+            for sid, s in b.streams.items():
+                if sid != cur.cuda_stream:
+                    ev = torch.cuda.Event()
+                    ev.record(s)
+                    cur.wait_event(ev)
+            b.streams = {}
         b.work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
     def _on_grad(self, p: torch.Tensor) -> None:
         if not self.require_sync:
             return
         b = self.buckets[self._owner[id(p)]]
+        if p.is_cuda:
+            s = torch.cuda.current_stream()
+            b.streams[s.cuda_stream] = s
         b.pending -= 1
         if b.pending == 0:
             self._launch(b)
@@ -120,7 +136,8 @@ class DataParallel(nn.Module):
         return _Ctx()
 
     def finish_gradients(self) -> None:
-        """Launch whatever has not been reduced yet, wait for all buckets, average."""
+        """Launch whatever has not been reduced yet, wait for all buckets, average (unless the optimizer folds 1/world).
+        Capturable: inside a CUDA-graph capture the collectives and the joins become graph nodes / edges."""
         if self.world == 1:
             return
         for b in self.buckets:
@@ -133,3 +150,10 @@ class DataParallel(nn.Module):
         if self.average:
             for g in self.groups:
                 g.g.mul_(1.0 / self.world)
+
+    def reset(self) -> None:
+        """Forget bucket progress (after a micro-batch that ran under ``no_sync`` nothing is pending anyway; this is for error paths)."""
+        for b in self.buckets:
+            b.work = None
+            b.pending = b.n_params
+            b.streams = {}

@@ -53,6 +53,26 @@ def check(M, C, use_gamma=True, use_res=True, use_rs=False, use_bias=True):
     return err
 
 
+def gelu_grad(pre):
+    return 0.5 * (1 + torch.erf(pre * 0.7071067811865476)) + pre * torch.exp(-0.5 * pre * pre) * 0.3989422804014327
+
+
+def check_bwd(M, C=96):
+    x, w1, b1, w2, b2, gamma, res = make(M, C)
+    g = torch.Generator(device=DEV).manual_seed(7)
+    dy = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    w2e = (w2.float() * gamma[:, None]).to(torch.bfloat16)
+    h, dpre, dx = F.mlp_fused_bwd(x, dy, w1, b1, w2e)
+    torch.cuda.synchronize()
+    pre = x.float() @ w1.float().t() + b1
+    h_ref = TF.gelu(pre)
+    dpre_ref = (dy.float() @ w2e.float()) * gelu_grad(pre)
+    dx_ref = dpre_ref.to(torch.bfloat16).float() @ w1.float()
+    errs = [float((a.float() - r).abs().max() / r.abs().max()) for a, r in ((h, h_ref), (dpre, dpre_ref), (dx, dx_ref))]
+    print(f"bwd M={M:7d} C={C}: rel err h {errs[0]:.3e} dpre {errs[1]:.3e} dx {errs[2]:.3e}", flush=True)
+    return max(errs)
+
+
 def timeit(fn, iters=20, flush=None):
     for _ in range(3):
         fn()
@@ -110,6 +130,24 @@ def main():
         print(f"C={C} M={M}: fused {t_f:.4f} ms ({bytes_alg / t_f / 1e6:.0f} GB/s algorithmic, {flops / t_f / 1e9:.0f} TFLOP/s) | two GEMMs {t_2:.4f} ms",
               flush=True)
     print("worst rel err (incl. bench shapes)", worst)
+    wb = 0.0
+    for M in (128, 300, 4113, 50000, 802816):
+        wb = max(wb, check_bwd(M))
+    print("worst bwd rel err", wb)
+    M, C = 802816, 96
+    x, w1, b1, w2, b2, gamma, res = make(M, C)
+    dy = torch.randn(M, C, device=DEV).to(torch.bfloat16)
+    w2e = (w2.float() * gamma[:, None]).to(torch.bfloat16)
+    t_b = timeit(lambda: F.mlp_fused_bwd(x, dy, w1, b1, w2e), flush=flush)
+    pre_dg = torch.empty(M, 4 * C, dtype=torch.bfloat16, device=DEV)
+
+    def two_b():
+        dpre = F.gemm(dy, w2e, M, 4 * C, C, b_trans=True, ldb=4 * C, act=F.ACT_MUL, act_grad_in=pre_dg)
+        F.gemm(dpre, w1, M, C, 4 * C, b_trans=True, ldb=C)
+
+    t_2b = timeit(two_b, flush=flush)
+    print(f"bwd data path C={C} M={M}: fused (recompute; writes h, dpre, dx) {t_b:.4f} ms ({11 * M * C * 2 / t_b / 1e6:.0f} GB/s) | dPre + dX GEMMs {t_2b:.4f} ms",
+          flush=True)
 
 
 if __name__ == "__main__":
