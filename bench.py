@@ -275,8 +275,9 @@ def run_b200(args):
 
     if args.mode == "train":
         lr = 1e-4 * (B * world) / 512.0  # linear LR scaling, schedule_utils.py:517-523
-        opt = FlatAdamW(model.named_parameters(), lr=lr, weight_decay=0.05, clip_grad=5.0, grad_scale=1.0)
-        dp = DataParallel(model, opt.flat, average=True) if world > 1 else None
+        # gradient averaging (DDP semantics) rides on the AdamW kernel: the all-reduce sums, grad_scale = 1 / world
+        opt = FlatAdamW(model.named_parameters(), lr=lr, weight_decay=0.05, clip_grad=5.0, grad_scale=1.0 / world)
+        dp = DataParallel(model, opt.flat, average=False) if world > 1 else None
         model.train()
         ts = TrainStep(model, opt, keys, nc, kind="ce", config=cfg, dp=dp)
         use_graph = not args.no_graph

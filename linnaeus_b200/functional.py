@@ -250,6 +250,19 @@ class _Mlp2(torch.autograd.Function):
         w1c = w1c if w1c is not None else compute_copy(w1, x2.dtype)
         w2c = w2c if w2c is not None else compute_copy(w2, x2.dtype)
         need_grad = grad_on and any(ctx.needs_input_grad)  # grad_on: see _Linear.forward
+        ctx.fused = False
+        if fused_mlp_ok(x2, K, Hd, N, act) and (not need_grad or K == 96):
+            # ConvNeXt pointwise pair in ONE kernel (hidden tile kept in TMEM); nothing but x is saved: the backward
+            # recomputes the pre-activation on the tensor cores (lnx_mlp_fused_bwd)
+            res2 = _c(residual).view(M, N) if residual is not None else None
+            y = mlp_fused_fwd(x2, w1c, b1, w2c, b2, gamma=col_scale, row_scale=row_scale, rows_per_group=rpg, residual=res2)
+            if need_grad:
+                ctx.fused = True
+                ctx.save_for_backward(x2, w1c, w2c, None, None, col_scale, w2, b2, row_scale)
+                ctx.rpg = rpg
+                ctx.params = (w1, b1, w2, b2, col_scale)
+                ctx.meta = (act, lead, K, Hd, N, residual is not None, x.shape)
+            return y.view(*lead, N)
         # GELU: the forward epilogue stores gelu'(pre) (one tanh serves both), so the backward epilogue is a multiply
         pre = torch.empty((M, Hd), dtype=x2.dtype, device=x2.device) if need_grad else None
         save_dg = need_grad and act == ACT_GELU
@@ -281,7 +294,11 @@ class _Mlp2(torch.autograd.Function):
         p_w1, p_b1, p_w2, p_b2, p_cs = ctx.params
         s_w1, s_b1, s_w2, s_b2 = _sink(p_w1), _sink(p_b1), _sink(p_w2), _sink(p_b2)
         db1 = s_b1 if s_b1 is not None else torch.zeros(Hd, dtype=torch.float32, device=dy2.device)
-        dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=ACT_MUL if ctx.save_dg else act, act_grad_in=pre)
+        dx_fused = None
+        if ctx.fused:
+            h, dpre, dx_fused = mlp_fused_bwd(x2, dy2, w1c, p_b1.detach() if p_b1 is not None else None, w2_eff)
+        else:
+            dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=ACT_MUL if ctx.save_dg else act, act_grad_in=pre)
         d_cs = dw2 = db2 = None
         if col_scale is not None:
             db2_raw = torch.zeros(N, dtype=torch.float32, device=dy2.device)
@@ -303,7 +320,10 @@ class _Mlp2(torch.autograd.Function):
         else:
             db2 = torch.zeros(N, dtype=torch.float32, device=dy2.device)
             dw2 = wgrad(dy2, h, db_out=db2)
-        dx = gemm(dpre, w1c, M, K, Hd, b_trans=True, ldb=K).view(xshape) if ctx.needs_input_grad[0] else None
+        if dx_fused is not None:
+            dx = dx_fused.view(xshape)
+        else:
+            dx = gemm(dpre, w1c, M, K, Hd, b_trans=True, ldb=K).view(xshape) if ctx.needs_input_grad[0] else None
         dw1 = None
         if s_w1 is not None:
             wgrad(dpre, x2, out=s_w1.view(Hd, K), db_out=db1)  # db1 = colsum(dpre) comes out of the same GEMM
