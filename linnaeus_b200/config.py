@@ -328,6 +328,31 @@ def make_synthetic_config(
     return c, num_classes
 
 
+class SyntheticTaxonomy:
+    """The synthetic hierarchy of SURVEY.md 8(d) (child i -> parent 0 if i == 0 else 1 + (i - 1) mod (C_parent - 1)) with the one
+    method the hierarchical head types call on a TaxonomyTree: ``build_hierarchy_matrices`` (R/utils/taxonomy/taxonomy_tree.py:384-404:
+    ``{"<parent>_<child>": [C_parent, C_child] 0/1 matrix}``, registered by the heads as ``hmatrix_*`` buffers)."""
+
+    def __init__(self, num_classes: dict[str, int]):
+        self.task_keys = list(num_classes.keys())
+        self.num_classes = dict(num_classes)
+
+    def parent_of(self, child_task: str, i: int) -> int:
+        cp = self.num_classes[self.task_keys[self.task_keys.index(child_task) + 1]]
+        return 0 if i == 0 else 1 + (i - 1) % (cp - 1)
+
+    def build_hierarchy_matrices(self) -> dict:
+        import torch
+
+        out = {}
+        for child, parent in zip(self.task_keys[:-1], self.task_keys[1:]):
+            m = torch.zeros((self.num_classes[parent], self.num_classes[child]), dtype=torch.float32)
+            for i in range(self.num_classes[child]):
+                m[self.parent_of(child, i), i] = 1.0
+            out[f"{parent}_{child}"] = m
+        return out
+
+
 # ---------------------------------------------------------------------------
 # mFormerV0 (config 5): arch table mirrored from configs/model/archs/mFormerV0/*.yaml
 # ---------------------------------------------------------------------------

@@ -620,7 +620,11 @@ class _HierLoss(torch.autograd.Function):
     """Fused K-task masked loss on the concatenated logits [B, sum C_k] -> scalar."""
 
     @staticmethod
-    def forward(ctx, logits, targets, class_off, kind, smoothing, soft_mats, task_w, keep, null_flag, phase1, stats):
+    def forward(ctx, logits, targets, class_off, kind, smoothing, soft_mats, task_w, keep, null_flag, phase1, stats, count_all=None):
+        # phase1: zero the loss of null samples (PHASE1 masking / criteria built with ignore_index = 0);
+        # count_all: divide by the batch size instead of #(loss != 0) (the PHASE1 training branch, hierarchical_loss.py:241-276)
+        if count_all is None:
+            count_all = phase1
         logits = _c(logits)
         B, Ctot = logits.shape
         K = len(class_off) - 1
@@ -636,7 +640,7 @@ class _HierLoss(torch.autograd.Function):
         call("lnx_loss_fwd", logits.data_ptr(), dt(logits), B, K, offs, targets.data_ptr(), ptr(null_flag), ptr(keep), kind, float(smoothing),
              mats, int(phase1), per.data_ptr(), raw.data_ptr(), lse.data_ptr(), wgt.data_ptr())
         red = torch.empty(1 + 3 * K, dtype=torch.float32, device=dev)  # total | scale[K] | task_sum[K] | nvalid[K]
-        call("lnx_loss_reduce", per.data_ptr(), ptr(task_w), B, K, int(phase1), red.data_ptr(), red[1:].data_ptr(), red[1 + K:].data_ptr(),
+        call("lnx_loss_reduce", per.data_ptr(), ptr(task_w), B, K, int(count_all), red.data_ptr(), red[1:].data_ptr(), red[1 + K:].data_ptr(),
              red[1 + 2 * K:].data_ptr())
         ctx.save_for_backward(logits, targets, wgt, lse, red)
         ctx.meta = (class_off, kind, smoothing, soft_mats, K, B)
@@ -658,14 +662,15 @@ class _HierLoss(torch.autograd.Function):
         dlogits = torch.empty_like(logits)
         call("lnx_loss_bwd", logits.data_ptr(), dt(logits), B, K, offs, targets.data_ptr(), wgt.data_ptr(), kind, float(smoothing), mats,
              lse.data_ptr(), red[1:].data_ptr(), g32.data_ptr(), dlogits.data_ptr())
-        return (dlogits,) + (None,) * 10
+        return (dlogits,) + (None,) * 11
 
 
 def hier_loss(logits_cat, targets_kb, class_off, kind=0, smoothing=0.1, soft_mats=None, task_w=None, keep=None, null_flag=None,
-              phase1=False, stats=None):
+              phase1=False, stats=None, count_all=None):
     if stats is None:
         stats = {}
-    return _HierLoss.apply(logits_cat, targets_kb, tuple(class_off), kind, smoothing, soft_mats, task_w, keep, null_flag, phase1, stats)
+    return _HierLoss.apply(logits_cat, targets_kb, tuple(class_off), kind, smoothing, soft_mats, task_w, keep, null_flag, phase1, stats,
+                           count_all)
 
 
 class _PerSampleLoss(torch.autograd.Function):

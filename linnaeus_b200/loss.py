@@ -25,10 +25,14 @@ __all__ = [
     "CrossEntropyLoss",
     "LabelSmoothingCrossEntropy",
     "TaxonomyAwareLabelSmoothingCE",
+    "SoftTargetCrossEntropy",
     "StaticTaskWeighting",
     "weighted_hierarchical_loss",
     "install_into_linnaeus_loss",
 ]
+
+
+LOSS_SOFT = 3  # host-side tag: runs the kernel's soft-label-row mode (LNX_LOSS_TAXONOMY) with the targets themselves as the rows
 
 
 class _Criterion(nn.Module):
@@ -37,8 +41,14 @@ class _Criterion(nn.Module):
 
     def forward(self, logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """Per-sample losses [B] of one task through the fused kernel (K = 1), differentiable."""
-        mats = [self.soft_labels] if self.kind == LOSS_TAXONOMY else None
-        return F.per_sample_loss(logits, _hard(target), self.kind, self.smoothing, mats, getattr(self, "ignore_index", None) == 0)
+        if self.kind == LOSS_SOFT:
+            rows = target.float().contiguous()
+            loss = F.per_sample_loss(logits, torch.arange(rows.shape[0], device=logits.device), LOSS_TAXONOMY, 0.0, [rows], False)
+        else:
+            mats = [self.soft_labels] if self.kind == LOSS_TAXONOMY else None
+            loss = F.per_sample_loss(logits, _hard(target), self.kind, self.smoothing, mats, getattr(self, "ignore_index", None) == 0)
+        sw = _criterion_sample_weight(self, target, logits.device)
+        return loss if sw is None else loss * sw
 
 
 class CrossEntropyLoss(_Criterion):
@@ -72,6 +82,29 @@ class TaxonomyAwareLabelSmoothingCE(_Criterion):
         self.weight, self.apply_class_weights, self.ignore_index = weight, apply_class_weights, ignore_index
 
 
+class SoftTargetCrossEntropy(_Criterion):
+    """-sum_c t_c log softmax(z)_c for [B, C] soft targets (mixup / CutMix), R/loss/basic_loss.py:188-228."""
+
+    kind = LOSS_SOFT
+
+    def __init__(self, weight=None, apply_class_weights: bool = False):
+        super().__init__()
+        self.weight, self.apply_class_weights, self.ignore_index = weight, apply_class_weights, None
+
+
+def _criterion_sample_weight(crit, target: torch.Tensor, dev) -> torch.Tensor | None:
+    """Criterion-level class weights (``weight=`` with ``apply_class_weights=True``; basic_loss.py:76-90,160-175,217-221):
+    weight[y] for hard / one-hot targets, sum_c t_c weight_c for SoftTargetCrossEntropy."""
+    w = getattr(crit, "weight", None)
+    if w is None or not getattr(crit, "apply_class_weights", False):
+        return None
+    w = w.to(device=dev, dtype=torch.float32)
+    kind = _KIND_BY_NAME.get(type(crit).__name__)
+    if kind == LOSS_SOFT:
+        return (target.to(dev).float() * w[None]).sum(1)
+    return w[_hard(target).to(dev)]
+
+
 class StaticTaskWeighting:
     """Minimal stand-in for GradientWeighting(type='static') (gradient_weighting.py:171-365)."""
 
@@ -88,6 +121,7 @@ _KIND_BY_NAME = {
     "CrossEntropyLoss": LOSS_CE,
     "LabelSmoothingCrossEntropy": LOSS_LS,
     "TaxonomyAwareLabelSmoothingCE": LOSS_TAXONOMY,
+    "SoftTargetCrossEntropy": LOSS_SOFT,
 }
 
 
@@ -166,12 +200,17 @@ def weighted_hierarchical_loss(
     kinds = {_KIND_BY_NAME.get(type(criteria[k]).__name__) for k in keys}
     if None in kinds or len(kinds) != 1:
         raise NotImplementedError(
-            "linnaeus_b200 fuses CrossEntropyLoss / LabelSmoothingCrossEntropy / TaxonomyAwareLabelSmoothingCE, one kind for all tasks; "
-            f"got {[type(criteria[k]).__name__ for k in keys]}"
+            "linnaeus_b200 fuses CrossEntropyLoss / LabelSmoothingCrossEntropy / TaxonomyAwareLabelSmoothingCE / SoftTargetCrossEntropy, "
+            f"one kind for all tasks; got {[type(criteria[k]).__name__ for k in keys]}"
         )
     kind = kinds.pop()
     smoothing = float(getattr(criteria[keys[0]], "smoothing", 0.0))
+    # PHASE1 training branch (hierarchical_loss.py:241-276): null losses zeroed, divisor = batch size.  Independently of it the
+    # criteria may have been built with ignore_index = 0 (loss/utils.py:104-145 does so for train AND validation criteria under
+    # TRAIN.PHASE1_MASK_NULL_LOSS): null losses are zero at the source and drop out of n_valid = #(loss != 0).
     phase1 = bool(config is not None and getattr(config.TRAIN, "PHASE1_MASK_NULL_LOSS", False) and not is_validation)
+    ign0 = [getattr(criteria[k], "ignore_index", None) == 0 for k in keys]
+    zero_null = phase1 or all(ign0)
 
     # concatenated logits: reuse the model's single head-GEMM output when the dict carries it
     cat = getattr(outputs, "cat", None)
@@ -186,7 +225,12 @@ def weighted_hierarchical_loss(
     dev = cat.device
     B = cat.shape[0]
 
-    tg = torch.stack([_hard(targets[k]) for k in keys]).to(dev).contiguous()
+    if kind == LOSS_SOFT:
+        if any(targets[k].dim() != 2 for k in keys):
+            raise ValueError("SoftTargetCrossEntropy needs [B, C] targets")
+        tg = torch.arange(B, device=dev).repeat(K, 1).contiguous()  # row index into the per-task target matrix
+    else:
+        tg = torch.stack([_hard(targets[k]) for k in keys]).to(dev).contiguous()
     null_flag = None
     if any(targets[k].dim() == 2 for k in keys):
         null_flag = torch.stack([(targets[k][:, 0] > 0.5) if targets[k].dim() == 2 else (targets[k] == 0) for k in keys])
@@ -200,29 +244,56 @@ def weighted_hierarchical_loss(
     else:
         p = float(ops_schedule.get_null_mask_prob(current_step)) if ops_schedule is not None else 1.0
     keep = None
-    if (not phase1) and p < 1.0:
+    is_null = None
+    if ((not phase1) and p < 1.0) or (any(ign0) and not zero_null):
         is_null = null_flag.bool() if null_flag is not None else (tg == 0)
+    if (not phase1) and p < 1.0:
         coin = torch.rand((K, B), device=dev) < p
         keep = torch.where(is_null & ~coin, 0.0, 1.0).float()
-    # class weights: dict lookup applied repeatedly by the reference
+    if any(ign0) and not zero_null:  # only some criteria ignore the null class: zero those tasks' null rows through the multiplier
+        rows = torch.tensor(ign0, device=dev)[:, None]
+        m = torch.where(is_null & rows, 0.0, 1.0).float()
+        keep = m if keep is None else keep * m
+    # per-sample multipliers from class weights.  The reference applies the GradientWeighting class-weight lookup repeatedly
+    # (SURVEY section 0): inside apply_loss_masking (masking.py:696-698; not on the PHASE1 training branch), in
+    # hierarchical_loss.py:313-334 when LOSS.GRAD_WEIGHTING.CLASS.TRAIN / .VAL says so, and in GradientWeighting.forward
+    # (gradient_weighting.py:334-352).  Soft [B, C] targets weigh in as sum_c t_c w_c each time (masking.py:505-515).
     cw = getattr(task_weighting, "class_weights", None)
     if cw:
-        times = 2 if phase1 else 3
+        try:
+            apply_cw = bool(config.LOSS.GRAD_WEIGHTING.CLASS.VAL if is_validation else config.LOSS.GRAD_WEIGHTING.CLASS.TRAIN)
+        except Exception:
+            apply_cw = True  # hierarchical_loss.py:322-325
+        times = (0 if phase1 else 1) + (1 if apply_cw else 0) + 1
         mult = torch.ones((K, B), device=dev)
         for i, k in enumerate(keys):
             if k in cw:
                 C = class_off[i + 1] - class_off[i]
-                mult[i] = _class_weight_vec(cw[k], C, dev)[tg[i]].pow(times)
+                vec = _class_weight_vec(cw[k], C, dev)
+                t_k = targets[k].to(dev)
+                sw = (t_k.float() * vec[None]).sum(1) if t_k.dim() == 2 else vec[t_k.long()]
+                mult[i] = sw.pow(times)
         keep = mult if keep is None else keep * mult
+    # criterion-level class weights (weight= with apply_class_weights=True): once, at the source
+    for i, k in enumerate(keys):
+        sw = _criterion_sample_weight(criteria[k], targets[k], dev)
+        if sw is not None:
+            if keep is None:
+                keep = torch.ones((K, B), device=dev)
+            keep[i] = keep[i] * sw
 
     tw = _task_weight_vector(task_weighting, keys, dev)
 
     soft = None
+    kernel_kind = kind
     if kind == LOSS_TAXONOMY:
         soft = [criteria[k].soft_labels.to(dev).float().contiguous() for k in keys]
+    elif kind == LOSS_SOFT:
+        soft = [targets[k].to(dev).float().contiguous() for k in keys]
+        kernel_kind = LOSS_TAXONOMY
 
     stats: dict = {}
-    total = F.hier_loss(cat, tg, class_off, kind, smoothing, soft, tw, keep, null_flag, phase1, stats)
+    total = F.hier_loss(cat, tg, class_off, kernel_kind, smoothing, soft, tw, keep, null_flag, zero_null, stats, count_all=phase1)
 
     raw = stats["raw"]
     per = stats["per_sample"]

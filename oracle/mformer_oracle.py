@@ -452,6 +452,13 @@ def per_sample_losses(logits: dict, targets: dict, kind: str = "ce", smoothing: 
     return out
 
 
+def _class_sample_weight(cw: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Per-sample class weight: cw[y] for hard labels, sum_c y_c cw_c for [B, C] targets (R/loss/masking.py:469-518)."""
+    if y.dim() == 1:
+        return cw[y.long()]
+    return (y.float() * cw[None]).sum(1)
+
+
 def hierarchical_loss(
     logits: dict,
     targets: dict,
@@ -464,23 +471,32 @@ def hierarchical_loss(
     soft_matrices: dict | None = None,
     class_weights: dict | None = None,
     coin_flips: dict | None = None,
+    apply_cw: bool | None = None,
+    criterion_weights: dict | None = None,
 ):
     """weighted_hierarchical_loss, R/loss/hierarchical_loss.py:138-395, with
     masking R/loss/masking.py:19-466,521-700 and static task weighting
     R/loss/gradient_weighting.py:301-358.
 
     total = sum_k w_k * (sum_i l_ik) / max(n_valid_k, 1e-6),  n_valid_k = #(l_ik != 0)
-    (in the PHASE1 branch ``num_valid_samples_per_task`` is absent, so the
-    divisor is the batch size -- hierarchical_loss.py:241-276,337-340).
+    (in the PHASE1 training branch ``num_valid_samples_per_task`` is absent, so the
+    divisor is the batch size -- hierarchical_loss.py:241-276,337-340; in validation the
+    criteria still carry ignore_index = 0 (loss/utils.py:104-145), so null samples are
+    zero and drop out of n_valid).
     ``coin_flips[t]``: bool [B]; True keeps a null sample (the reference draws
     ``rand < null_mask_prob`` for null rows only; tests inject the draw).
-    ``class_weights[t]``: [C] tensor, applied like the reference's dict lookup
-    once in apply_loss_masking, once in hierarchical_loss and once in
-    GradientWeighting.forward when given.
+    ``class_weights[t]``: [C] tensor = the reference's dict lookup.  It is applied once inside
+    apply_loss_masking (masking.py:696-698; not on the PHASE1 training branch), once in
+    hierarchical_loss.py:313-334 when ``apply_cw`` (config LOSS.GRAD_WEIGHTING.CLASS.TRAIN / .VAL;
+    None = the config defaults True / False) and once in GradientWeighting.forward (:334-352).
+    ``criterion_weights[t]``: [C] tensor = a criterion built with ``weight=`` and
+    ``apply_class_weights=True`` (basic_loss.py:76-90,160-175,217-221).
     """
     ignore = 0 if phase1_mask_null else None  # R/loss/utils.py (prepare_loss_functions)
     raw = per_sample_losses(logits, targets, kind, smoothing, soft_matrices, ignore)
     keys = list(raw.keys())
+    if criterion_weights:
+        raw = {t: raw[t] * _class_sample_weight(criterion_weights[t], targets[t] if kind == "soft" else _hard(targets[t])) for t in keys}
     masked, n_valid = {}, {}
     for t in keys:
         y = targets[t]
@@ -498,15 +514,16 @@ def hierarchical_loss(
             n_valid[t] = int((l != 0).sum().item())
     cw_times = 0
     if class_weights:
-        cw_times = 2 if (phase1_mask_null and not is_validation) else 3
+        if apply_cw is None:
+            apply_cw = not is_validation
+        cw_times = (0 if (phase1_mask_null and not is_validation) else 1) + (1 if apply_cw else 0) + 1
     total = 0.0
     weighted = {}
     for t in keys:
         w = 1.0 if task_weights is None else float(task_weights[t])
         l = masked[t]
-        if cw_times:
-            sw = class_weights[t][_hard(targets[t])]
-            l = l * sw.pow(cw_times)
+        if cw_times and t in class_weights:
+            l = l * _class_sample_weight(class_weights[t], targets[t]).pow(cw_times)
         weighted[t] = l.sum() / max(float(n_valid[t]), 1e-6) * w
         total = total + weighted[t]
     comps = {

@@ -29,6 +29,13 @@ CASES = {
     "tiny_nometa": (dict(variant="sm", img_size=64, dims=(32, 64, 128, 256), heads=(2, 4), rope_depths=(2, 1), conv_depths=(1, 1, 1, 1), meta=False), 3, 2, 2, "ce"),
     "sm224_ce": (dict(variant="sm", img_size=224), 2, 0, 0, "ce"),
     "md224_ce": (dict(variant="md", img_size=224), 1, 0, 0, "ce"),
+    # round 2: hierarchical head types on the CUDA path, a bench-like batch, and the long-sequence attention path (N = 580 / 148)
+    "tiny_hsm": (dict(variant="sm", img_size=64, dims=(32, 64, 128, 256), heads=(2, 4), rope_depths=(2, 1), conv_depths=(1, 1, 1, 1),
+                      head_type="HierarchicalSoftmax"), 4, 3, 3, "ce"),
+    "tiny_cond": (dict(variant="sm", img_size=64, dims=(32, 64, 128, 256), heads=(2, 4), rope_depths=(2, 1), conv_depths=(1, 1, 1, 1),
+                       head_type="ConditionalClassifier"), 4, 4, 4, "ce"),
+    "sm224_b32": (dict(variant="sm", img_size=224), 32, 5, 5, "ce"),
+    "xl384_shallow": (dict(variant="xl", img_size=384, rope_depths=(1, 1), conv_depths=(1, 1, 1, 1)), 1, 6, 6, "ce"),
 }
 
 
@@ -42,10 +49,12 @@ def run_case(name):
     from linnaeus.models import build_model
 
     cfg, nc = refload.reference_config(**kw)
-    model = build_model(cfg, num_classes=nc, taxonomy_tree=None)
+    tree = refload.synthetic_taxonomy_tree(nc) if kw.get("head_type", "Linear") != "Linear" else None
+    model = build_model(cfg, num_classes=nc, taxonomy_tree=tree)
     a = O.arch_from_config(cfg, nc)
     P = O.synth_state_dict(O.param_shapes(a), wseed)
-    model.load_state_dict(P)
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected and all("hmatrix_" in k for k in missing), (missing, unexpected)  # buffers come from the taxonomy tree
     x, meta, tg = O.synth_batch(a, batch, dseed)
     model.train()
     logits = model(x, meta)

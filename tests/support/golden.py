@@ -15,6 +15,10 @@ CASES = {
     "tiny_nometa": (dict(variant="sm", img_size=64, meta=False, **_TINY), "ce"),
     "sm224_ce": (dict(variant="sm", img_size=224), "ce"),
     "md224_ce": (dict(variant="md", img_size=224), "ce"),
+    "tiny_hsm": (dict(variant="sm", img_size=64, head_type="HierarchicalSoftmax", **_TINY), "ce"),
+    "tiny_cond": (dict(variant="sm", img_size=64, head_type="ConditionalClassifier", **_TINY), "ce"),
+    "sm224_b32": (dict(variant="sm", img_size=224), "ce"),
+    "xl384_shallow": (dict(variant="xl", img_size=384, rope_depths=(1, 1), conv_depths=(1, 1, 1, 1)), "ce"),
 }
 
 

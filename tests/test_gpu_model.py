@@ -15,17 +15,29 @@ DEV = "cuda"
 ZERO_GRAD = {"aggregate.bias"}
 
 
+def oracle_leaf(n: str) -> str:
+    """Name of the oracle leaf holding parameter ``n`` (hierarchical head types share one ModuleDict of per-level classifiers:
+    the model lists it under the first head, the oracle's functional forward reads level t through head.<t>.<sub>.<t>)."""
+    parts = n.split(".")
+    if parts[0] == "head" and len(parts) == 5:
+        return ".".join(["head", parts[3], parts[2], parts[3], parts[4]])
+    return n
+
+
 def _setup(name):
     import linnaeus_b200 as L
     from oracle import mformer_oracle as O
+    from linnaeus_b200.config import SyntheticTaxonomy
     from tests.support.golden import load_case
 
     cfg, nc, kind, z = load_case(name)
     a = O.arch_from_config(cfg, nc)
     P = O.synth_state_dict(O.param_shapes(a), int(z["wseed"]))
     x, meta, tg = O.synth_batch(a, int(z["batch"]), int(z["dseed"]))
-    model = L.build_model(cfg, nc)
-    model.load_state_dict(P)
+    hier = a.head_type != "Linear"
+    model = L.build_model(cfg, nc, taxonomy_tree=SyntheticTaxonomy(nc) if hier else None)
+    missing, unexpected = model.load_state_dict(P, strict=not hier)
+    assert not unexpected and all("hmatrix_" in k for k in missing)  # hierarchy buffers come from the taxonomy, not the checkpoint
     model = model.to(DEV)
     return L, O, cfg, nc, kind, z, a, P, x, meta, tg, model
 
@@ -76,47 +88,74 @@ def _check(name, dtype, rtol):
         head = torch.from_numpy(z[f"ghead/{n}"])
         e2 = float((g[: head.numel()] - head).abs().max() / (head.abs().max() + 1e-3 * gmax / max(1.0, g.numel() ** 0.5)))
         if dtype == torch.bfloat16:
-            e2 = 0.0  # element-wise bf16 gradients are checked as full vectors in test_bf16_gradients_vs_fp32_mode
+            e2 = 0.0  # element-wise bf16 gradients are checked as full vectors in test_bf16_gradients_vs_oracle
+        elif n.startswith("meta_") and int(z["batch"]) >= 32:
+            # one ReLU input of a metadata head within ~1e-7 of zero lands on the other side (measured: sm224_b32, one unit of
+            # meta_spatial_head_2.3.w1; its tensors move by 5e-3 relative L2, every other tensor stays at 1e-6): norm only
+            e2 = 0.0
         if max(e, e2) > worst[0]:
             worst = (max(e, e2), n)
-    assert worst[0] <= (5 * rtol if dtype == torch.bfloat16 else 3 * rtol), worst
+    # measured (tools/diag_parity.py): fp32 norms within 8e-5 of the reference's, elements within 6e-6; bf16 norms within 3.2e-2
+    assert worst[0] <= (5 * rtol if dtype == torch.bfloat16 else rtol), worst
     return model, a, P, x, meta, tg, out
 
 
-@pytest.mark.parametrize("name", ["tiny_ce", "tiny_taxonomy", "tiny_nometa", "sm224_ce", "md224_ce"])
+FP32_CASES = ["tiny_ce", "tiny_taxonomy", "tiny_nometa", "sm224_ce", "md224_ce", "tiny_hsm", "tiny_cond", "sm224_b32", "xl384_shallow"]
+BF16_CASES = ["tiny_ce", "sm224_ce", "tiny_hsm", "tiny_cond", "sm224_b32", "xl384_shallow"]
+
+
+@pytest.mark.parametrize("name", FP32_CASES)
 def test_fp32_mode_matches_reference_golden(name):
+    """fp32 mode: loss, logits, every gradient norm and the first 32 elements of every gradient within 1e-4 of the unmodified
+    reference (goldens).  tiny_hsm / tiny_cond run the HierarchicalSoftmax / ConditionalClassifier head types on the CUDA path;
+    xl384_shallow the long-sequence attention kernels (N = 580 and 148, head_dim 64, 16 / 32 heads); sm224_b32 a batch of 32."""
     _check(name, torch.float32, 1e-4)
 
 
-@pytest.mark.parametrize("name", ["tiny_ce", "sm224_ce"])
+@pytest.mark.parametrize("name", BF16_CASES)
 def test_bf16_mode_matches_reference_golden(name):
     _check(name, torch.bfloat16, 2e-2)
 
 
-@pytest.mark.parametrize("name", ["tiny_ce", "sm224_ce"])
-def test_bf16_gradients_vs_fp32_mode(name):
-    """bf16 mode (tcgen05 GEMMs + attention) against the fp32 mode of the same CUDA model (itself 1e-4 from the
-    reference): relative L2 error of every full gradient tensor.  Stated tolerance: median <= 2e-2, and no tensor
-    above 2e-1 (with a batch of 2-4 samples, ReLU masks of the tiny metadata heads flip under bf16 rounding, which
-    makes those few small tensors noisier than the 2e-2 bulk)."""
+# bf16 gradients whose error is not rounding noise of a long dot product but a discrete event or a tiny tensor:
+#  meta_*           Linear -> ReLU -> LN -> ResNorm on a [B, 2..10] input: ReLU masks flip under bf16 rounding of the pre-activation,
+#                   which moves whole rows of these small gradients (measured up to 1.4e-1 relative L2 at B = 2..32)
+#  *.attn.freqs     [2, heads, 32] rotary frequencies: the gradient is a sum over all tokens of products of small differences
+#                   (measured up to 3.0e-2)
+#  aggregate.weight two scalars (measured 3.4e-2 on xl384_shallow)
+BF16_GRAD_ALLOW = (("meta_", 2e-1), (".attn.freqs", 4e-2), ("aggregate.weight", 4e-2))
+
+
+@pytest.mark.parametrize("name", BF16_CASES)
+def test_bf16_gradients_vs_oracle(name):
+    """bf16 mode against the CPU oracle (fp32; pinned to the unmodified reference by tests/test_oracle_vs_reference.py and the
+    goldens): relative L2 error of EVERY full gradient tensor.  Stated tolerance: at least 90 % of the tensors outside the allow-list
+    within 2e-2, none of them above 3e-2 (measured worst 2.4e-2: a 32-element LayerNorm weight), allow-listed tensors within
+    their own bound."""
     L, O, cfg, nc, kind, z, a, P, x, meta, tg, model = _setup(name)
-    grads = {}
-    for dtype in (torch.float32, torch.bfloat16):
-        model.zero_grad(set_to_none=True)
-        model.set_compute_dtype(dtype).train()
-        out, total = _loss(L, O, model, a, kind, x, meta, tg, cfg)
-        total.backward()
-        grads[dtype] = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
-    gmax = max(float(g.norm()) for g in grads[torch.float32].values())
+    leaves = {n: t.clone().requires_grad_(True) for n, t in P.items()}
+    lo = O.forward(leaves, a, x, meta)
+    to, _ = O.hierarchical_loss(lo, tg, kind=kind, soft_matrices=O.synthetic_taxonomy_smoothing(a.tasks) if kind == "taxonomy" else None)
+    to.backward()
+    model.set_compute_dtype(torch.bfloat16).train()
+    out, total = _loss(L, O, model, a, kind, x, meta, tg, cfg)
+    total.backward()
+    gmax = max(float(leaves[oracle_leaf(n)].grad.norm()) for n, _ in model.named_parameters())
     errs = []
-    for n, g32 in grads[torch.float32].items():
+    for n, p in model.named_parameters():
         if n in ZERO_GRAD:
             continue
-        e = float((grads[torch.bfloat16][n] - g32).norm() / (g32.norm() + 1e-4 * gmax))
-        errs.append((e, n))
+        ref = leaves[oracle_leaf(n)].grad
+        e = float((p.grad.detach().float().cpu() - ref).norm() / (ref.norm() + 1e-4 * gmax))
+        bound = 3e-2
+        for pat, b in BF16_GRAD_ALLOW:
+            if pat in n:
+                bound = b
+        assert e <= bound, (n, e, bound)
+        if bound == 3e-2:
+            errs.append(e)
     errs.sort()
-    assert errs[len(errs) // 2][0] <= 2e-2, errs[len(errs) // 2]
-    assert errs[-1][0] <= 2e-1, errs[-5:]
+    assert errs[int(0.9 * len(errs))] <= 2e-2, errs[int(0.9 * len(errs))]
 
 
 def test_fp32_all_grads_match_oracle_elementwise():
@@ -295,3 +334,82 @@ def test_gradnorm_task_gradient_norms_match_oracle_autograd(with_optimizer):
     out, total = _loss(L, O, model, a, kind, x, meta, tg, cfg)
     total.backward()
     assert abs(float(total.detach()) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+
+
+def _tiny_train_setup(seed=0, B=8, lr=2e-2):
+    import linnaeus_b200 as L
+    from linnaeus_b200.optim import FlatAdamW
+
+    torch.manual_seed(seed)
+    cfg, nc = L.make_synthetic_config("sm", 64, dims=(32, 64, 128, 256), heads=(2, 4), rope_depths=(1, 1), conv_depths=(1, 1, 1, 1), n_tasks=3)
+    model = L.build_model(cfg, nc).to(DEV).set_compute_dtype(torch.float32).train()
+    keys = list(nc.keys())
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, 3, 64, 64, generator=g).to(DEV)
+    meta = torch.randn(B, 15, generator=g).to(DEV)
+    tg = {k: torch.randint(1, nc[k], (B,), generator=g).to(DEV) for k in keys}
+    opt = FlatAdamW(model.named_parameters(), lr=lr, clip_grad=5.0)
+    return cfg, nc, keys, model, opt, x, meta, tg
+
+
+def test_graph_replay_equals_eager_steps_and_capture_leaves_state_untouched():
+    """Three optimizer steps through the captured CUDA graph == three eager steps from the same start (fp32 mode: the same kernels in
+    the same order, so parameters must agree to rounding); capture() itself - warm-up iterations included - must not move the
+    parameters, the Adam state or the step count, and state_dict() reports the true step count after replays."""
+    from linnaeus_b200.engine import TrainStep
+
+    cfg, nc, keys, m_e, opt_e, x, meta, tg = _tiny_train_setup()
+    _, _, _, m_g, opt_g, _, _, _ = _tiny_train_setup()
+    ts_e = TrainStep(m_e, opt_e, keys, nc, kind="ce", config=cfg)
+    ts_g = TrainStep(m_g, opt_g, keys, nc, kind="ce", config=cfg)
+    before = {n: p.detach().clone() for n, p in m_g.named_parameters()}
+    ts_g.capture(x, meta, tg, warmup=2)
+    torch.cuda.synchronize()
+    for n, p in m_g.named_parameters():
+        assert torch.equal(p.detach(), before[n]), n
+    assert opt_g.step_count() == 0 and all(float(f.m.abs().sum()) == 0.0 for f in opt_g.flat if f is not None)
+    for i in range(3):
+        xi = x.roll(i, 0)
+        le = ts_e.step(xi, meta, tg)
+        lg = ts_g.replay(xi, meta, tg)
+        assert abs(float(le) - float(lg)) <= 1e-5 * abs(float(le)), i
+    # Adam normalises the update, so an element whose gradient is ~0 turns atomics-order noise into an O(lr) difference:
+    # compare the UPDATES tensor by tensor in relative L2
+    for (n, a), (_, b) in zip(m_e.named_parameters(), m_g.named_parameters()):
+        if n in ZERO_GRAD or n.endswith("attn.qkv.bias"):  # true gradient exactly 0 (aggregate.bias; the key third of the qkv bias)
+            continue
+        upd = float((a.detach() - before[n]).norm())
+        assert float((a - b).norm()) <= 2e-3 * upd + 1e-7, (n, float((a - b).norm()), upd)
+    sd = opt_g.state_dict()
+    assert int(sd["state"][0]["step"]) == 3 and opt_g.step_count() == 3
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_gradient_accumulation_matches_one_large_batch(graph):
+    """accum_steps = 2 over two half batches == one step on the full batch (R/train.py:173-192: loss / accum, optimizer step on the
+    boundary only); no null labels, so the per-task means of the halves average to the full-batch mean."""
+    from linnaeus_b200.engine import TrainStep
+
+    cfg, nc, keys, m_f, opt_f, x, meta, tg = _tiny_train_setup(seed=3)
+    _, _, _, m_a, opt_a, _, _, _ = _tiny_train_setup(seed=3)
+    start = {n: p.detach().clone() for n, p in m_f.named_parameters()}
+    TrainStep(m_f, opt_f, keys, nc, kind="ce", config=cfg).step(x, meta, tg)
+    ts = TrainStep(m_a, opt_a, keys, nc, kind="ce", config=cfg, accum_steps=2)
+    h = x.shape[0] // 2
+    halves = [(x[:h], meta[:h], {k: v[:h] for k, v in tg.items()}), (x[h:], meta[h:], {k: v[h:] for k, v in tg.items()})]
+    if graph:
+        ts.capture(*halves[0], warmup=1)
+        before = [p.detach().clone() for p in m_a.parameters()]
+        ts.replay(*halves[0])
+        torch.cuda.synchronize()
+        assert all(torch.equal(p.detach(), b) for p, b in zip(m_a.parameters(), before))  # micro-batch: no optimizer step
+        ts.replay(*halves[1])
+    else:
+        ts.step(*halves[0])
+        ts.step(*halves[1])
+    assert opt_a.step_count() == 1
+    for (n, a), (_, b) in zip(m_f.named_parameters(), m_a.named_parameters()):
+        if n in ZERO_GRAD or n.endswith("attn.qkv.bias"):
+            continue
+        upd = float((a.detach() - start[n]).norm())  # see the note on Adam in the test above
+        assert float((a - b).norm()) <= 5e-3 * upd + 1e-7, (n, float((a - b).norm()), upd)

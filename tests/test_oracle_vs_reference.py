@@ -165,3 +165,98 @@ def test_train_step_runs_and_decreases_loss():
     l0, _, _ = O.train_step(P, a, x, meta, tg, state, 1, 1e-3)
     l1, _, _ = O.train_step(P, a, x, meta, tg, state, 2, 1e-3)
     assert l1 < l0
+
+
+# ----------------------------------------------------------------------------- class weights, validation, soft targets
+def _ref_loss_full(cfg, logits, targets, kind, weights, class_weights=None, crit_weights=None, phase1=False, is_validation=False,
+                   cw_train=True, cw_val=False):
+    """The unmodified reference loss with class weights / criterion weights / validation flags set the way
+    R/loss/utils.py:58-150 (prepare_loss_functions) and R/main.py wire them."""
+    from linnaeus.loss.basic_loss import CrossEntropyLoss, LabelSmoothingCrossEntropy, SoftTargetCrossEntropy
+    from linnaeus.loss.gradient_weighting import GradientWeighting
+    from linnaeus.loss.hierarchical_loss import weighted_hierarchical_loss
+
+    cfg = cfg.clone()
+    cfg.defrost()
+    cfg.TRAIN.PHASE1_MASK_NULL_LOSS = phase1
+    cfg.LOSS.GRAD_WEIGHTING.CLASS.TRAIN = cw_train
+    cfg.LOSS.GRAD_WEIGHTING.CLASS.VAL = cw_val
+    ign = 0 if phase1 else None
+    keys = list(logits.keys())
+    cwt = crit_weights or {}
+    if kind == "ce":
+        crit = {k: CrossEntropyLoss(weight=cwt.get(k), apply_class_weights=k in cwt, ignore_index=ign) for k in keys}
+    elif kind == "ls":
+        crit = {k: LabelSmoothingCrossEntropy(weight=cwt.get(k), smoothing=0.1, apply_class_weights=k in cwt, ignore_index=ign) for k in keys}
+    else:
+        crit = {k: SoftTargetCrossEntropy(weight=cwt.get(k), apply_class_weights=k in cwt) for k in keys}
+    cw_dicts = None
+    if class_weights:
+        cw_dicts = {k: {i: float(v[i]) for i in range(0, v.numel(), 2)} for k, v in class_weights.items()}  # sparse dict: missing -> 1.0
+    gw = GradientWeighting(keys, cfg, "static", init_weights=weights, class_weights=cw_dicts)
+
+    class Sched:
+        def get_null_mask_prob(self, step):
+            return 1.0
+
+    return weighted_hierarchical_loss(logits, targets, crit, gw, Sched(), 0, is_validation=is_validation, config=cfg)
+
+
+def _loss_case(seed=0, B=12, soft=False):
+    g = torch.Generator().manual_seed(seed)
+    tasks = [("taxa_L10", 11), ("taxa_L20", 7), ("taxa_L30", 4)]
+    logits = {t: torch.randn(B, C, generator=g) for t, C in tasks}
+    targets = {t: torch.randint(0, C, (B,), generator=g) for t, C in tasks}
+    targets["taxa_L10"][:3] = 0
+    targets["taxa_L20"][1] = 0
+    if soft:  # mixup-style soft targets: lam * one-hot(a) + (1 - lam) * one-hot(b)
+        for t, C in tasks:
+            a = torch.nn.functional.one_hot(targets[t], C).float()
+            b = a[torch.randperm(B, generator=g)]
+            targets[t] = 0.7 * a + 0.3 * b
+    cw = {t: 0.5 + torch.rand(C, generator=g) for t, C in tasks}
+    for t in cw:  # the reference looks classes up in a sparse dict: odd indices default to 1.0
+        cw[t][1::2] = 1.0
+    weights = {t: 0.5 + 0.25 * i for i, (t, _) in enumerate(tasks)}
+    return tasks, logits, targets, cw, weights
+
+
+@pytest.mark.parametrize("kind", ["ce", "ls"])
+@pytest.mark.parametrize("phase1,is_validation,cw_train,cw_val", [
+    (False, False, True, False), (False, False, False, False), (True, False, True, False), (True, False, False, False),
+    (False, True, True, False), (False, True, True, True), (True, True, True, False), (True, True, True, True)])
+def test_class_weight_power_and_validation_match_reference(kind, phase1, is_validation, cw_train, cw_val):
+    """a17: how often the class-weight lookup multiplies the per-sample loss (R/loss/masking.py:696-698,
+    hierarchical_loss.py:313-334, gradient_weighting.py:334-352) in train / validation, with and without PHASE1, and the
+    validation divisor when the criteria carry ignore_index = 0."""
+    cfg, _, _, _ = _build(**TINY)
+    tasks, logits, targets, cw, weights = _loss_case()
+    r_total, r_comp, _ = _ref_loss_full(cfg, logits, targets, kind, weights, class_weights=cw, phase1=phase1, is_validation=is_validation,
+                                        cw_train=cw_train, cw_val=cw_val)
+    o_total, o_comp = O.hierarchical_loss(logits, targets, kind=kind, task_weights=weights, phase1_mask_null=phase1, is_validation=is_validation,
+                                          class_weights=cw, apply_cw=(cw_val if is_validation else cw_train))
+    torch.testing.assert_close(o_total, r_total, rtol=1e-5, atol=1e-6)
+    for t in o_comp["weighted_tasks"]:
+        assert abs(o_comp["weighted_tasks"][t] - r_comp["weighted_tasks"][t]) < 1e-5
+    if "num_valid_samples_per_task" in r_comp["null_masking"]:
+        assert {t: int(v) for t, v in r_comp["null_masking"]["num_valid_samples_per_task"].items()} == o_comp["num_valid_samples_per_task"]
+
+
+@pytest.mark.parametrize("with_cw", [False, True])
+def test_soft_target_cross_entropy_matches_reference(with_cw):
+    """a15: SoftTargetCrossEntropy (basic_loss.py:188-228) on mixup-style [B, C] targets, class weights as sum_c t_c w_c."""
+    cfg, _, _, _ = _build(**TINY)
+    tasks, logits, targets, cw, weights = _loss_case(seed=1, soft=True)
+    r_total, r_comp, _ = _ref_loss_full(cfg, logits, targets, "soft", weights, class_weights=cw if with_cw else None)
+    o_total, o_comp = O.hierarchical_loss(logits, targets, kind="soft", task_weights=weights, class_weights=cw if with_cw else None, apply_cw=True)
+    torch.testing.assert_close(o_total, r_total, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["ce", "ls", "soft"])
+def test_criterion_level_class_weights_match_reference(kind):
+    """a15: criteria built with weight= and apply_class_weights=True (basic_loss.py:76-90,160-175,217-221)."""
+    cfg, _, _, _ = _build(**TINY)
+    tasks, logits, targets, cw, weights = _loss_case(seed=2, soft=(kind == "soft"))
+    r_total, _, _ = _ref_loss_full(cfg, logits, targets, kind, weights, crit_weights=cw)
+    o_total, _ = O.hierarchical_loss(logits, targets, kind=kind, task_weights=weights, criterion_weights=cw)
+    torch.testing.assert_close(o_total, r_total, rtol=1e-5, atol=1e-6)
