@@ -93,3 +93,26 @@ def test_checkpoints_interchange_with_the_reference_model(arch, tmp_path):
     assert not missing and not unexpected
     for k, v in ours.state_dict().items():
         assert torch.equal(ref.state_dict()[k], v), k
+
+
+def test_roundtrip_through_the_data_parallel_wrapper(tmp_path):
+    """linnaeus_b200.DataParallel exposes ``module.``-prefixed keys like torch's DDP: a checkpoint saved through the wrapper loads
+    back into the wrapper AND into the bare model, and a bare checkpoint loads into the wrapper (the reference
+    decides from the target model's own keys, R/utils/checkpoint.py:798-830)."""
+    from linnaeus_b200.flat import FlatGroup
+    from linnaeus_b200.parallel import DataParallel
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.LayerNorm(3))
+    dp = DataParallel(net, [FlatGroup(list(net.parameters()), with_state=False)])
+    assert all(k.startswith("module.") for k in dp.state_dict())
+    p_wrapped = C.save_checkpoint(str(tmp_path / "w"), dp, None, epoch=1)
+    p_bare = C.save_checkpoint(str(tmp_path / "b"), net, None, epoch=1)
+    want = {k: v.clone() for k, v in net.state_dict().items()}
+    for path in (p_wrapped, p_bare):
+        for target_wrapped in (True, False):
+            net2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.LayerNorm(3))
+            tgt = DataParallel(net2, [FlatGroup(list(net2.parameters()), with_state=False)]) if target_wrapped else net2
+            C.load_checkpoint(path, tgt, strict=True)
+            for k, v in net2.state_dict().items():
+                assert torch.equal(v, want[k]), (path, target_wrapped, k)
