@@ -196,8 +196,11 @@ int lnx_loss_bwd(const void* logits, int dtype, int B, int K, const int* class_o
                  const float* lse, const float* scale, const float* gscale, void* dlogits, lnx_stream_t s);
 
 /* ---- optimizer (R/train.py:282-313, R/optimizers/build.py:67-106) -------- */
-/* sumsq[0] += sum g^2  (call once per flat buffer, zero sumsq first) */
-int lnx_sumsq(const float* g, int64_t n, float* sumsq, lnx_stream_t s);
+/* sumsq[0] += sum g^2  (call once per flat buffer, zero sumsq first).  workspace: NULL (fp32 atomics: the last bits depend on
+ * block scheduling) or LNX_SUMSQ_WORKSPACE floats, zero before the first call: per-block partials added in index order by the last
+ * block, i.e. a deterministic norm -> data-parallel replicas compute bit-identical clip coefficients and stay in lock step. */
+#define LNX_SUMSQ_WORKSPACE 1024
+int lnx_sumsq(const float* g, int64_t n, float* sumsq, float* workspace, lnx_stream_t s);
 /* norm_out[0] = sqrt(sumsq * gscale^2); coef_out[0] = clip > 0 ? min(1, clip/(norm+1e-6)) : 1 */
 int lnx_clip_coef(const float* sumsq, float gscale, float clip, float* norm_out, float* coef_out, lnx_stream_t s);
 /* AdamW (decoupled decay) on a flat buffer; g is multiplied by gscale*coef[0] first.

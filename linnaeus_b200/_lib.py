@@ -66,7 +66,7 @@ SIGNATURES = {
     "lnx_loss_fwd": [P, I, I, I, P, P, P, P, I, F, P, I, P, P, P, P, P],
     "lnx_loss_reduce": [P, P, I, I, I, P, P, P, P, P],
     "lnx_loss_bwd": [P, I, I, I, P, P, P, I, F, P, P, P, P, P, P],
-    "lnx_sumsq": [P, L, P, P],
+    "lnx_sumsq": [P, L, P, P, P],
     "lnx_clip_coef": [P, F, F, P, P, P],
     "lnx_adamw": [P, P, P, P, L, F, F, F, F, F, F, F, F, P, P, P, P],
 }

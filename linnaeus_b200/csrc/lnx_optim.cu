@@ -7,8 +7,12 @@ using namespace lnx;
 
 namespace {
 
-__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+// ws (optional): [0] ticket counter (zero on entry, left zero), [1 .. gridDim.x] per-block partial sums.  With a workspace the
+// last block to finish adds the partials in index order, so the result does not depend on block scheduling: data-parallel
+// replicas compute bit-identical clip coefficients from bit-identical gradients and stay in lock step.
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out, float* __restrict__ ws) {
   __shared__ float red[32];
+  __shared__ bool last;
   float acc = 0.f;
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -25,7 +29,28 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
   if (threadIdx.x < 32) {
     float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) atomicAdd(out, t);
+    if (threadIdx.x == 0) {
+      if (!ws) {
+        atomicAdd(out, t);
+      } else {
+        ws[1 + blockIdx.x] = t;
+        __threadfence();
+        const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(ws), 1u);
+        last = ticket == gridDim.x - 1;
+      }
+    }
+  }
+  if (!ws) return;
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += __ldcg(ws + 1 + i);  // fixed order per lane, fixed shuffle tree
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      out[0] += t;
+      *reinterpret_cast<unsigned*>(ws) = 0u;
+    }
   }
 }
 
@@ -81,12 +106,12 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 
 }  // namespace
 
-extern "C" int lnx_sumsq(const float* g, int64_t n, float* sumsq, lnx_stream_t s) {
+extern "C" int lnx_sumsq(const float* g, int64_t n, float* sumsq, float* workspace, lnx_stream_t s) {
   LNX_REQUIRE(g && sumsq, LNX_ERR_NULL);
   LNX_REQUIRE(n > 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(lnx_aligned16(g), LNX_ERR_ALIGN);
   const int blocks = (int)max(1LL, min((long long)kNumSMs * 4, ((long long)n / 4 + 255) / 256));
-  sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(g, n, sumsq);
+  sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)s>>>(g, n, sumsq, workspace);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }

@@ -117,12 +117,15 @@ class TrainStep:
 
         self._graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count
-        with torch.cuda.graph(self._graph):
+        # thread-local capture mode: NCCL's watchdog thread polls CUDA events of earlier collectives; in the default global mode a
+        # query from ANY thread invalidates the capture
+        mode = "thread_local" if self.dp is not None else "global"
+        with torch.cuda.graph(self._graph, capture_error_mode=mode):
             self._static_loss = self._iteration(si, sm, st, True)
         self.launches_per_step = _lib.launch_count - n0  # C-ABI kernel launches recorded in the boundary graph
         if self.accum_steps > 1:
             self._graph_micro = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_micro, pool=self._graph.pool()):
+            with torch.cuda.graph(self._graph_micro, pool=self._graph.pool(), capture_error_mode=mode):
                 self._static_loss_micro = self._iteration(si, sm, st, False)
         # capture executes nothing, but the warm-up iterations did: put the training state back
         with torch.no_grad():

@@ -58,6 +58,7 @@ class FlatAdamW(torch.optim.Optimizer):
         self.grad_scale = float(grad_scale)  # e.g. 1/world_size folded into the update
         self._step = 0
         self._scratch = torch.zeros(3, dtype=torch.float32, device=dev)  # sumsq | norm | coef
+        self._norm_ws = torch.zeros(1024, dtype=torch.float32, device=dev)  # LNX_SUMSQ_WORKSPACE: deterministic global norm
         self._step_dev = torch.zeros(1, dtype=torch.float32, device=dev)  # device-side step count (CUDA-graph safe)
         self._lr_dev: torch.Tensor | None = None
 
@@ -95,7 +96,7 @@ class FlatAdamW(torch.optim.Optimizer):
         sc[0:1].zero_()
         for f in self.flat:
             if f is not None:
-                call("lnx_sumsq", f.g.data_ptr(), f.numel, sc.data_ptr())
+                call("lnx_sumsq", f.g.data_ptr(), f.numel, sc.data_ptr(), self._norm_ws.data_ptr())
         call("lnx_clip_coef", sc.data_ptr(), self.grad_scale, self.clip_grad, sc[1:].data_ptr(), sc[2:].data_ptr())
         for g, f in zip(self.param_groups, self.flat):
             if f is None:

@@ -31,7 +31,7 @@ class _Bucket:
         self.group, self.lo, self.hi, self.n_params = group, lo, hi, n_params
         self.pending = n_params
         self.work = None
-        self.streams = {}  # CUDA streams that produced gradients of this bucket (the metadata branch runs on a side stream)
+        self.streams = {}  # stream id -> last "gradient written" event of every CUDA stream that produced gradients of this bucket
 
 
 def plan_buckets(groups: list[FlatGroup], bucket_bytes: int) -> tuple[list[_Bucket], dict[int, int]]:
@@ -71,6 +71,7 @@ class DataParallel(nn.Module):
         self.overlap = overlap
         self.require_sync = True
         self.buckets, self._owner = plan_buckets(self.groups, int(bucket_mb * (1 << 20)))
+        self._seen: set[int] = set()
         self._hooks = []
         if self.world > 1 and overlap:
             for g in self.groups:
@@ -100,24 +101,29 @@ class DataParallel(nn.Module):
     def _launch(self, b: _Bucket) -> None:
         buf = self.groups[b.group].g[b.lo:b.hi]
         if buf.is_cuda and b.streams:
-            # NCCL orders the collective after the CURRENT stream only: join every other stream that wrote gradients of this
-            # bucket (under CUDA-graph capture the event pair becomes a graph edge)
-            cur = torch.cuda.current_stream()
-            for sid, s in b.streams.items():
-                if sid != cur.cuda_stream:
-                    ev = torch.cuda.Event()
-                    ev.record(s)
-                    cur.wait_event(ev)
+            # NCCL orders the collective after the CURRENT stream only: wait for the last gradient write of every other stream
+            # that produced gradients of this bucket (under CUDA-graph capture the event pair becomes a graph edge)
+            cur = torch.cuda.current_stream().cuda_stream
+            for sid, ev in b.streams.items():
+                if sid != cur:
+                    torch.cuda.current_stream().wait_event(ev)
             b.streams = {}
         b.work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
     def _on_grad(self, p: torch.Tensor) -> None:
         if not self.require_sync:
             return
+        # one notification per parameter and iteration: a kernel that accumulates straight into p.grad reports through
+        # p._lnx_grad_ready, and autograd's post-accumulate hook can fire for the same parameter later in the same backward
+        if id(p) in self._seen:
+            return
+        self._seen.add(id(p))
         b = self.buckets[self._owner[id(p)]]
-        if p.is_cuda:
+        if p.is_cuda and self.world > 1:
             s = torch.cuda.current_stream()
-            b.streams[s.cuda_stream] = s
+            ev = torch.cuda.Event()
+            ev.record(s)  # marks "this parameter's gradient is written" on the producing stream; a later event on the same stream subsumes it
+            b.streams[s.cuda_stream] = ev
         b.pending -= 1
         if b.pending == 0:
             self._launch(b)
@@ -147,6 +153,8 @@ class DataParallel(nn.Module):
             b.work.wait()
             b.work = None
             b.pending = b.n_params
+            b.streams = {}
+        self._seen.clear()
         if self.average:
             for g in self.groups:
                 g.g.mul_(1.0 / self.world)
@@ -157,3 +165,4 @@ class DataParallel(nn.Module):
             b.work = None
             b.pending = b.n_params
             b.streams = {}
+        self._seen.clear()

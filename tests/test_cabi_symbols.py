@@ -66,7 +66,7 @@ def test_argument_validation_needs_no_gpu(lib):
     """Null / shape checks run before any CUDA call, so they are testable on CPU."""
     assert lib.lnx_layernorm_fwd(None, None, None, None, None, None, None, 4, 32, 1e-5, 0, None) == -6
     assert lib.lnx_gemm(1, None, 8, 0, None, 8, 0, None, 1, 4, 4, 4, None, 0, None, None, None, None, None, 0, None, 0, 0, None) == -6
-    assert lib.lnx_sumsq(None, 8, None, None) == -6
+    assert lib.lnx_sumsq(None, 8, None, None, None) == -6
     buf = (ctypes.c_float * 64)()
     p = ctypes.addressof(buf)
     assert lib.lnx_layernorm_fwd(p, p, p, None, p, None, None, 0, 32, 1e-5, 0, None) == -1  # rows == 0
