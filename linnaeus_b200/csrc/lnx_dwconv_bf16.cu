@@ -158,6 +158,139 @@ __global__ void __launch_bounds__(NTHREADS, NS == 2 ? 3 : 2)
   }
 }
 
+// ------------------------------------------------------------------ forward, 4 output rows per lane
+// Same lane layout (channel pair x half strip of 7 columns), but a warp owns FOUR output rows of a 28 x 14 tile and walks the
+// INPUT rows: every pixel loaded from shared memory feeds all the (output row, filter row) pairs that touch it, so the
+// shared-memory loads per FFMA2 drop from 1 / 3.0 to 1 / 6.3 (the 14 x 14 / 2-row kernel re-reads each input row once per filter
+// row and is co-limited by the issue slots and the shared-memory pipe at 45 % of the FMA rate).  The 49 taps do not fit in
+// registers next to 28 accumulators, so the filter rows are split in two passes (kh 0-3, kh 4-6) with their taps reloaded per pass.
+constexpr int R4_ROWS = 28;                 // tile rows: 7 warps x 4
+constexpr int R4_HALO_H = R4_ROWS + 6;      // 34
+constexpr int R4_HALO_BYTES = R4_HALO_H * HALO * CC * 2;  // 34 x 20 x 32 ch x 2 B = 43 520
+
+template <int KH0, int KH1>
+__device__ __forceinline__ void dw_r4_pass(const uint32_t* __restrict__ tp, const float2* __restrict__ wsm, int p, float2 (&acc)[4][7]) {
+  float2 wk[KH1 - KH0][7];
+#pragma unroll
+  for (int kh = KH0; kh < KH1; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw) wk[kh - KH0][kw] = wsm[(kh * 7 + kw) * PW + p];
+#pragma unroll
+  for (int ir = KH0; ir < KH1 + 3; ++ir) {  // input row relative to the warp's first output row: ir = rr + kh
+    const uint32_t* rowp = tp + ir * HALO * PW;
+#pragma unroll
+    for (int ix = 0; ix < 13; ++ix) {
+      const float2 v = unpack_bf16x2(rowp[ix * PW]);
+#pragma unroll
+      for (int kh = KH0; kh < KH1; ++kh) {
+        const int rr = ir - kh;
+        if (rr >= 0 && rr < 4) {
+#pragma unroll
+          for (int kw = 0; kw < 7; ++kw) {
+            const int o = ix - kw;
+            if (o >= 0 && o < 7) acc[rr][o] = ffma2(v, wk[kh - KH0][kw], acc[rr][o]);
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+    dwconv7_fwd_r4_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w49c, const float* __restrict__ bias,
+                          const bf16* __restrict__ res, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = smem_raw;                                                   // [2][34][20][CC] bf16
+  float2* wsm = reinterpret_cast<float2*>(smem_raw + 2 * R4_HALO_BYTES);             // [49][PW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * R4_HALO_BYTES + 49 * CC * 4);
+  uint64_t* empty = full + 2;
+
+  const int c0 = blockIdx.y * CC;
+  const int total = B * tiles_h * tiles_w;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], NWARPS);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) reinterpret_cast<float*>(wsm)[i] = w49c[(i / CC) * C + c0 + (i % CC)];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto coord = [&](int t, int& b, int& h0, int& w0) {
+    const int tw = t % tiles_w;
+    t /= tiles_w;
+    w0 = tw * TILE;
+    h0 = (t % tiles_h) * R4_ROWS;
+    b = t / tiles_h;
+  };
+  if (warp == NWARPS) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait_relaxed(&empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        int b, h0, w0;
+        coord(t, b, h0, w0);
+        mbar_expect_tx(&full[buf], R4_HALO_BYTES);
+        tma_load_4d(tiles + buf * R4_HALO_BYTES, &tmX, &full[buf], c0, w0 - 3, h0 - 3, b);
+      }
+    }
+    return;
+  }
+  const int p = lane & (PW - 1);
+  const int col0 = (lane >> 4) * 7;
+  const int orow0 = warp * 4;
+  float2 bv = make_float2(0.f, 0.f);
+  if (bias) bv = *reinterpret_cast<const float2*>(bias + c0 + 2 * p);
+
+  int it = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    const int buf = it & 1;
+    int b, h0, w0;
+    coord(t, b, h0, w0);
+    mbar_wait(&full[buf], ((uint32_t)it >> 1) & 1u);
+    const bool active = h0 + orow0 < H;
+    float2 acc[4][7];
+    if (active) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int o = 0; o < 7; ++o) acc[rr][o] = bv;
+      const uint32_t* tp = reinterpret_cast<const uint32_t*>(tiles + buf * R4_HALO_BYTES) + ((orow0 * HALO + col0) * PW + p);
+      dw_r4_pass<0, 4>(tp, wsm, p, acc);
+      dw_r4_pass<4, 7>(tp, wsm, p, acc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[buf]);
+    if (active) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int hh = h0 + orow0 + rr;
+        if (hh < H) {
+          const long long off = (((long long)b * H + hh) * W + w0 + col0) * C + c0 + 2 * p;
+          bf16* yrow = y + off;
+          if (res) {
+#pragma unroll
+            for (int o = 0; o < 7; ++o)
+              if (w0 + col0 + o < W) {
+                const float2 rv = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(res + off + (long long)o * C)));
+                acc[rr][o].x += rv.x;
+                acc[rr][o].y += rv.y;
+              }
+          }
+#pragma unroll
+          for (int o = 0; o < 7; ++o)
+            if (w0 + col0 + o < W)
+              *reinterpret_cast<__nv_bfloat162*>(yrow + (long long)o * C) = __floats2bfloat162_rn(acc[rr][o].x, acc[rr][o].y);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ weight gradient
 __global__ void __launch_bounds__(NTHREADS, 2)
     dwconv7_wgrad_x2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, float* __restrict__ dw49c,
@@ -271,11 +404,33 @@ int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, co
                          cudaStream_t st) {
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 7u)) return LNX_ERR_ALIGN;
   if (C % CC != 0) return LNX_ERR_SHAPE;
+  const int chunks = C / CC;
+  const int tiles_w = (W + TILE - 1) / TILE;
+  // LNX_DWCONV_KERNEL: 4 = four output rows per lane (28 x 14 tiles, default when the image has at least 28 rows), 2 / 3 = the
+  // two-row kernel with a 2- or 3-deep halo ring
+  static const int sel = getenv("LNX_DWCONV_KERNEL") ? atoi(getenv("LNX_DWCONV_KERNEL")) : 4;
+  if (sel == 4 && H >= 20) {
+    CUtensorMap tmX;
+    if (!make_nhwc_tmap(&tmX, x, B, H, W, C, HALO, R4_HALO_H)) return LNX_ERR_UNSUPPORTED;
+    const int tiles_h = (H + R4_ROWS - 1) / R4_ROWS;
+    const size_t smem = 2 * (size_t)R4_HALO_BYTES + 49 * CC * 4 + 64;
+    static bool attr4 = false;
+    if (!attr4) {
+      cudaError_t e = cudaFuncSetAttribute(dwconv7_fwd_r4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return lnx_set_cuda_error(e);
+      attr4 = true;
+    }
+    const int total = B * tiles_h * tiles_w;
+    const int gx = max(1, min(total, (kNumSMs * 2 + chunks - 1) / chunks));
+    dwconv7_fwd_r4_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
+    LNX_CHECK_LAUNCH();
+    return LNX_OK;
+  }
   CUtensorMap tmX;
   if (!make_nhwc_tmap(&tmX, x, B, H, W, C, HALO, HALO)) return LNX_ERR_UNSUPPORTED;
-  const int tiles_w = (W + TILE - 1) / TILE, tiles_h = (H + TILE - 1) / TILE;
-  static const int ns = getenv("LNX_DWCONV_STAGES") ? atoi(getenv("LNX_DWCONV_STAGES")) : 2;
-  const size_t smem = (size_t)(ns == 3 ? 3 : 2) * HALO_BYTES + 49 * CC * 4 + 64;
+  const int tiles_h = (H + TILE - 1) / TILE;
+  const int ns = sel == 3 ? 3 : 2;
+  const size_t smem = (size_t)ns * HALO_BYTES + 49 * CC * 4 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = ns == 3 ? cudaFuncSetAttribute(dwconv7_fwd_x2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -283,7 +438,6 @@ int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, co
     if (e != cudaSuccess) return lnx_set_cuda_error(e);
     attr_set = true;
   }
-  const int chunks = C / CC;
   const int total = B * tiles_h * tiles_w;
   const int gx = max(1, min(total, (kNumSMs * (ns == 3 ? 2 : 3) + chunks - 1) / chunks));
   if (ns == 3)
