@@ -495,10 +495,10 @@ def roofline_table(cx: Ctx, B: int, step_ms: float, hbm: float, tf_sus: float):
     db = torch.zeros(C0, device=dev)
     conv_flops = 2.0 * 49 * M0 * C0
     add(f"dwconv7_fwd_x2_kernel {B}x56x56x96 (forward; the data gradient is the same kernel + fused skip)",
-        lambda: cx.lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), bias.data_ptr(), None, y.data_ptr(), B, 56, 56, C0, 1), 6, "fp32-fma",
+        lambda: cx.lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), 0, bias.data_ptr(), None, y.data_ptr(), B, 56, 56, C0, 1), 6, "fp32-fma",
         alg_bytes=2 * M0 * C0 * 2, flops=conv_flops)
     add(f"dwconv7_wgrad_x2_kernel {B}x56x56x96",
-        lambda: cx.lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), db.data_ptr(), B, 56, 56, C0, 1), 3, "fp32-fma",
+        lambda: cx.lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), 0, db.data_ptr(), B, 56, 56, C0, 1), 3, "fp32-fma",
         alg_bytes=2 * M0 * C0 * 2, flops=conv_flops)
     # ---- stage 0: fused pointwise pair
     x2 = x.view(M0, C0)

@@ -72,6 +72,12 @@ int lnx_colsum(const void* x, float* out, int64_t M, int N, int dtype, lnx_strea
 int lnx_cast_f32_to_bf16(const float* in, void* out, int64_t n, lnx_stream_t s);
 /* out[m,:] = x[m,:] * s[m / rows_per_group]  (DropPath backward: per-sample mask on the branch gradient) */
 int lnx_rowscale(const void* x, const float* s, void* out, int64_t M, int N, int rows_per_group, int dtype, lnx_stream_t st);
+/* ConvNeXt layer scale y = gamma * (h W2^T + b2) (R/models/blocks/convnext.py:84): out[n,:] = bf16(w[n,:] * cs[n]) is the weight
+ * with gamma folded in for the data-gradient GEMM; lnx_layerscale_bwd turns the UN-scaled gradients into the parameter gradients
+ * dw[N,K] += cs dw_raw, db[N] += cs db_raw, dcs[N] += rowsum(dw_raw * w) + b db_raw (db_raw / b / db may be NULL). */
+int lnx_rowscale_cast_bf16(const float* w, const float* cs, void* out, int N, int K, lnx_stream_t s);
+int lnx_layerscale_bwd(const float* dw_raw, const float* db_raw, const float* w, const float* b, const float* cs, float* dw, float* db,
+                       float* dcs, int N, int K, lnx_stream_t s);
 /* out = dy * act'(pre)  (single-layer Linear+activation backward; act = LNX_ACT_GELU | LNX_ACT_RELU) */
 int lnx_act_bwd(const void* dy, const void* pre, void* out, int64_t n, int act, int dtype, lnx_stream_t s);
 
@@ -87,13 +93,17 @@ int lnx_layernorm_bwd(const void* dy, const void* x, const float* w, const float
                       float* dw, float* db, int64_t rows, int C, int dtype, lnx_stream_t s);
 
 /* ---- depthwise 7x7 (pad 3) on NHWC ------------------------------------- */
-/* w49c is the Conv2d weight [C,1,7,7] transposed to [49,C]; bias may be NULL.
- * The data gradient is the same call with the taps reversed and bias = NULL.
+/* w_layout: LNX_DW_W_TAP_MAJOR = [49, C]; LNX_DW_W_NATIVE = the Conv2d weight itself, [C,1,7,7] = [C, 49]; LNX_DW_W_NATIVE_FLIPPED =
+ * the same memory read with the taps reversed.  bias may be NULL.  The data gradient is the same call on dY with the taps reversed
+ * and bias = NULL; `residual` (nullable) is added to the result (the skip-connection gradient when run as the data gradient).
  * R/models/blocks/convnext.py:56-58,76. */
-int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, const void* residual, void* y, int B, int H, int W, int C, int dtype,
-                    lnx_stream_t s);
-/* dw49c[49,C] += , dbias[C] += */
-int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, int dtype, lnx_stream_t s);
+enum { LNX_DW_W_TAP_MAJOR = 0, LNX_DW_W_NATIVE = 1, LNX_DW_W_NATIVE_FLIPPED = 2 };
+int lnx_dwconv7_fwd(const void* x, const float* w, int w_layout, const float* bias, const void* residual, void* y, int B, int H, int W, int C,
+                    int dtype, lnx_stream_t s);
+/* dw += (layout LNX_DW_W_TAP_MAJOR or LNX_DW_W_NATIVE: the native layout lets the kernel accumulate straight into the parameter's
+ * gradient buffer), dbias[C] += */
+int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw, int w_layout, float* dbias, int B, int H, int W, int C, int dtype,
+                      lnx_stream_t s);
 
 /* ---- GEMM with fused epilogue ------------------------------------------ */
 /* Weight (+ bias) gradient of y = x W^T + b on the tensor cores, reduction over the M rows (tokens):

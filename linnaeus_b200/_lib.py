@@ -34,10 +34,12 @@ SIGNATURES = {
     "lnx_colsum": [P, P, L, I, I, P],
     "lnx_cast_f32_to_bf16": [P, P, L, P],
     "lnx_act_bwd": [P, P, P, L, I, I, P],
+    "lnx_rowscale_cast_bf16": [P, P, P, I, I, P],
+    "lnx_layerscale_bwd": [P, P, P, P, P, P, P, P, I, I, P],
     "lnx_layernorm_fwd": [P, P, P, P, P, P, P, L, I, F, I, P],
     "lnx_layernorm_bwd": [P, P, P, P, P, P, P, P, P, L, I, I, P],
-    "lnx_dwconv7_fwd": [P, P, P, P, P, I, I, I, I, I, P],
-    "lnx_dwconv7_wgrad": [P, P, P, P, I, I, I, I, I, P],
+    "lnx_dwconv7_fwd": [P, P, I, P, P, P, I, I, I, I, I, P],
+    "lnx_dwconv7_wgrad": [P, P, P, I, P, I, I, I, I, I, P],
     "lnx_gemm": [I, P, L, I, P, L, I, P, I, I, I, I, P, I, P, P, P, P, P, I, P, I, I, P],
     "lnx_wgrad": [P, L, P, L, P, P, L, I, I, I, P],
     "lnx_mlp_fused_fwd": [P, P, P, P, P, P, P, I, P, P, L, I, I, P],

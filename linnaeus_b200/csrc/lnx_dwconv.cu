@@ -64,12 +64,17 @@ __device__ __forceinline__ void load_tile(T* tile, const T* __restrict__ src, in
   }
 }
 
+// weight element (tap, channel) in the caller's layout (see include/linnaeus_b200.h: LNX_DW_W_*)
+__device__ __forceinline__ long long widx(int wl, int tap, int c, int C) {
+  return wl == 0 ? (long long)tap * C + c : (long long)c * 49 + (wl == 2 ? 48 - tap : tap);
+}
+
 // ------------------------------------------------------------------ forward
 template <typename T, int CPL>
 __global__ void __launch_bounds__(NWARPS * 32) dwconv7_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w49c,
                                                                    const float* __restrict__ bias, const T* __restrict__ res,
                                                                    T* __restrict__ y, int B, int H, int W, int C, int tiles_w,
-                                                                   int tiles_h) {
+                                                                   int tiles_h, int wl) {
   constexpr int CC = 32 * CPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);                                     // [20][20][CC]
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(NWARPS * 32) dwconv7_fwd_kernel(const T* __res
   const int b = t / tiles_h;
   const int h0 = th * TILE, w0 = tw * TILE;
 
-  for (int i = threadIdx.x; i < 49 * CC; i += blockDim.x) wsm[i] = w49c[(i / CC) * C + c0 + (i % CC)];
+  for (int i = threadIdx.x; i < 49 * CC; i += blockDim.x) wsm[i] = w49c[widx(wl, i / CC, c0 + (i % CC), C)];
   load_tile<T>(tile, x, b, h0, w0, c0, H, W, C, CC, HALO, HALO, 3, 3);
   __syncthreads();
 
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(NWARPS * 32) dwconv7_fwd_kernel(const T* __res
 template <typename T, int CPL>
 __global__ void __launch_bounds__(NWARPS * 32) dwconv7_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                      float* __restrict__ dw49c, float* __restrict__ dbias, int B, int H,
-                                                                     int W, int C, int tiles_w, int tiles_h) {
+                                                                     int W, int C, int tiles_w, int tiles_h, int wl) {
   constexpr int CC = 32 * CPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);                       // [20][20][CC]
@@ -231,13 +236,13 @@ __global__ void __launch_bounds__(NWARPS * 32) dwconv7_wgrad_kernel(const T* __r
 #pragma unroll
   for (int q = 0; q < CPL; ++q) atomicAdd(&red[49 * CC + cl + q], bacc[q]);
   __syncthreads();
-  for (int i = threadIdx.x; i < 49 * CC; i += blockDim.x) atomicAdd(dw49c + (i / CC) * C + c0 + (i % CC), red[i]);
+  for (int i = threadIdx.x; i < 49 * CC; i += blockDim.x) atomicAdd(dw49c + widx(wl, i / CC, c0 + (i % CC), C), red[i]);
   if (dbias)
     for (int i = threadIdx.x; i < CC; i += blockDim.x) atomicAdd(dbias + c0 + i, red[49 * CC + i]);
 }
 
 template <typename T, int CPL>
-int fwd_launch(const void* x, const float* w49c, const float* bias, const void* res, void* y, int B, int H, int W, int C, cudaStream_t st) {
+int fwd_launch(const void* x, const float* w49c, int wl, const float* bias, const void* res, void* y, int B, int H, int W, int C, cudaStream_t st) {
   constexpr int CC = 32 * CPL;
   const int tiles_w = (W + TILE - 1) / TILE, tiles_h = (H + TILE - 1) / TILE;
   const size_t smem = sizeof(T) * HALO * HALO * CC + sizeof(float) * 49 * CC;
@@ -245,13 +250,13 @@ int fwd_launch(const void* x, const float* w49c, const float* bias, const void* 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return lnx_set_cuda_error(e);
   dim3 grid(B * tiles_h * tiles_w, C / CC);
-  kern<<<grid, NWARPS * 32, smem, st>>>((const T*)x, w49c, bias, (const T*)res, (T*)y, B, H, W, C, tiles_w, tiles_h);
+  kern<<<grid, NWARPS * 32, smem, st>>>((const T*)x, w49c, bias, (const T*)res, (T*)y, B, H, W, C, tiles_w, tiles_h, wl);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
 
 template <typename T, int CPL>
-int wgrad_launch(const void* x, const void* dy, float* dw, float* db, int B, int H, int W, int C, cudaStream_t st) {
+int wgrad_launch(const void* x, const void* dy, float* dw, int wl, float* db, int B, int H, int W, int C, cudaStream_t st) {
   constexpr int CC = 32 * CPL;
   const int tiles_w = (W + TILE - 1) / TILE, tiles_h = (H + TILE - 1) / TILE;
   const size_t smem = sizeof(T) * (HALO * HALO + TILE * TILE) * CC + sizeof(float) * 50 * CC;
@@ -262,7 +267,7 @@ int wgrad_launch(const void* x, const void* dy, float* dw, float* db, int B, int
   const int total_tiles = B * tiles_h * tiles_w;
   int gx = max(1, min(total_tiles, (kNumSMs * 2 + chunks - 1) / chunks));
   dim3 grid(gx, chunks);
-  kern<<<grid, NWARPS * 32, smem, st>>>((const T*)x, (const T*)dy, dw, db, B, H, W, C, tiles_w, tiles_h);
+  kern<<<grid, NWARPS * 32, smem, st>>>((const T*)x, (const T*)dy, dw, db, B, H, W, C, tiles_w, tiles_h, wl);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
@@ -270,30 +275,33 @@ int wgrad_launch(const void* x, const void* dy, float* dw, float* db, int B, int
 }  // namespace
 
 // bf16: packed-fp32x2 (FFMA2) kernels of lnx_dwconv_bf16.cu
-int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, const void* res, void* y, int B, int H, int W, int C,
+int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, int wl, const float* bias, const void* res, void* y, int B, int H, int W, int C,
                          cudaStream_t st);
-int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, cudaStream_t st);
+int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, int wl, float* dbias, int B, int H, int W, int C, cudaStream_t st);
 
-extern "C" int lnx_dwconv7_fwd(const void* x, const float* w49c, const float* bias, const void* residual, void* y, int B, int H, int W, int C,
-                               int dtype, lnx_stream_t s) {
-  LNX_REQUIRE(x && w49c && y, LNX_ERR_NULL);
-  LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0, LNX_ERR_SHAPE);
+extern "C" int lnx_dwconv7_fwd(const void* x, const float* w, int w_layout, const float* bias, const void* residual, void* y, int B, int H, int W,
+                               int C, int dtype, lnx_stream_t s) {
+  LNX_REQUIRE(x && w && y, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0 && w_layout >= 0 && w_layout <= 2, LNX_ERR_SHAPE);
   LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(y), LNX_ERR_ALIGN);
   cudaStream_t st = (cudaStream_t)s;
   const bool pair = (C % 64 == 0);
   if (dtype == LNX_F32)
-    return pair ? fwd_launch<float, 2>(x, w49c, bias, residual, y, B, H, W, C, st) : fwd_launch<float, 1>(x, w49c, bias, residual, y, B, H, W, C, st);
-  if (dtype == LNX_BF16) return lnx_dwconv7_fwd_bf16(x, w49c, bias, residual, y, B, H, W, C, st);
+    return pair ? fwd_launch<float, 2>(x, w, w_layout, bias, residual, y, B, H, W, C, st)
+                : fwd_launch<float, 1>(x, w, w_layout, bias, residual, y, B, H, W, C, st);
+  if (dtype == LNX_BF16) return lnx_dwconv7_fwd_bf16(x, w, w_layout, bias, residual, y, B, H, W, C, st);
   return LNX_ERR_DTYPE;
 }
 
-extern "C" int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, int dtype, lnx_stream_t s) {
-  LNX_REQUIRE(x && dy && dw49c, LNX_ERR_NULL);
-  LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0, LNX_ERR_SHAPE);
+extern "C" int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw, int w_layout, float* dbias, int B, int H, int W, int C, int dtype,
+                                 lnx_stream_t s) {
+  LNX_REQUIRE(x && dy && dw, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 32 == 0 && (w_layout == 0 || w_layout == 1), LNX_ERR_SHAPE);
   LNX_REQUIRE(lnx_aligned16(x) && lnx_aligned16(dy), LNX_ERR_ALIGN);
   cudaStream_t st = (cudaStream_t)s;
   const bool pair = (C % 64 == 0);
-  if (dtype == LNX_F32) return pair ? wgrad_launch<float, 2>(x, dy, dw49c, dbias, B, H, W, C, st) : wgrad_launch<float, 1>(x, dy, dw49c, dbias, B, H, W, C, st);
-  if (dtype == LNX_BF16) return lnx_dwconv7_wgrad_bf16(x, dy, dw49c, dbias, B, H, W, C, st);
+  if (dtype == LNX_F32)
+    return pair ? wgrad_launch<float, 2>(x, dy, dw, w_layout, dbias, B, H, W, C, st) : wgrad_launch<float, 1>(x, dy, dw, w_layout, dbias, B, H, W, C, st);
+  if (dtype == LNX_BF16) return lnx_dwconv7_wgrad_bf16(x, dy, dw, w_layout, dbias, B, H, W, C, st);
   return LNX_ERR_DTYPE;
 }

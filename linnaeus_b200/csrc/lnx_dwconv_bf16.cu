@@ -35,6 +35,12 @@ constexpr int HALO_BYTES = HALO * HALO * CC * 2;  // 25600
 constexpr int CENTER_BYTES = TILE * TILE * CC * 2;  // 12544
 constexpr int CENTER_PAD = 12800;                   // keeps every buffer 256-byte aligned
 
+// weight element (tap, channel) in the caller's layout: 0 = [49][C] tap-major, 1 = the Conv2d weight itself [C][49], 2 = [C][49] read with the
+// taps reversed (the data gradient convolves dY with the flipped filter)
+__device__ __forceinline__ long long widx(int wl, int tap, int c, int C) {
+  return wl == 0 ? (long long)tap * C + c : (long long)c * 49 + (wl == 2 ? 48 - tap : tap);
+}
+
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
@@ -55,7 +61,7 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_w, int tiles_h)
 template <int NS>  // halo-tile ring depth: 2 (three CTAs per SM) or 3 (two CTAs per SM; a full tile of compute between load and use)
 __global__ void __launch_bounds__(NTHREADS, NS == 2 ? 3 : 2)
     dwconv7_fwd_x2_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w49c, const float* __restrict__ bias,
-                          const bf16* __restrict__ res, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h) {
+                          const bf16* __restrict__ res, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h, int wl) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* tiles = smem_raw;                                              // [2][20][20][CC] bf16
   float2* wsm = reinterpret_cast<float2*>(smem_raw + NS * HALO_BYTES);           // [49][PW]
@@ -72,7 +78,7 @@ __global__ void __launch_bounds__(NTHREADS, NS == 2 ? 3 : 2)
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) reinterpret_cast<float*>(wsm)[i] = w49c[(i / CC) * C + c0 + (i % CC)];
+  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) reinterpret_cast<float*>(wsm)[i] = w49c[widx(wl, i / CC, c0 + (i % CC), C)];
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -198,7 +204,7 @@ __device__ __forceinline__ void dw_r4_pass(const uint32_t* __restrict__ tp, cons
 
 __global__ void __launch_bounds__(NTHREADS, 2)
     dwconv7_fwd_r4_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w49c, const float* __restrict__ bias,
-                          const bf16* __restrict__ res, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h) {
+                          const bf16* __restrict__ res, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h, int wl) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* tiles = smem_raw;                                                   // [2][34][20][CC] bf16
   float2* wsm = reinterpret_cast<float2*>(smem_raw + 2 * R4_HALO_BYTES);             // [49][PW]
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) reinterpret_cast<float*>(wsm)[i] = w49c[(i / CC) * C + c0 + (i % CC)];
+  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) reinterpret_cast<float*>(wsm)[i] = w49c[widx(wl, i / CC, c0 + (i % CC), C)];
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 // ------------------------------------------------------------------ weight gradient
 __global__ void __launch_bounds__(NTHREADS, 2)
     dwconv7_wgrad_x2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, float* __restrict__ dw49c,
-                            float* __restrict__ dbias, int B, int H, int W, int C, int tiles_w, int tiles_h) {
+                            float* __restrict__ dbias, int B, int H, int W, int C, int tiles_w, int tiles_h, int wl) {
   constexpr int STAGE = HALO_BYTES + CENTER_PAD;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* stages = smem_raw;                                        // [2]{x halo [20][20][CC], dy [14][14][CC]}
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
     atomicAdd(&red[49 * CC + 2 * p + 1], bacc.y);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) atomicAdd(dw49c + (i / CC) * C + c0 + (i % CC), red[i]);
+  for (int i = threadIdx.x; i < 49 * CC; i += NTHREADS) atomicAdd(dw49c + widx(wl, i / CC, c0 + (i % CC), C), red[i]);
   if (dbias)
     for (int i = threadIdx.x; i < CC; i += NTHREADS) atomicAdd(dbias + c0 + i, red[49 * CC + i]);
 }
@@ -400,16 +406,16 @@ bool make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C
 
 }  // namespace
 
-int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, const void* res, void* y, int B, int H, int W, int C,
+int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, int wl, const float* bias, const void* res, void* y, int B, int H, int W, int C,
                          cudaStream_t st) {
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 7u)) return LNX_ERR_ALIGN;
   if (C % CC != 0) return LNX_ERR_SHAPE;
   const int chunks = C / CC;
   const int tiles_w = (W + TILE - 1) / TILE;
-  // LNX_DWCONV_KERNEL: 4 = four output rows per lane (28 x 14 tiles, default when the image has at least 28 rows), 2 / 3 = the
+  // LNX_DWCONV_KERNEL: 4 = four output rows per lane (28 x 14 tiles; measured faster only for large images: used when H >= 64), 2 / 3 = the
   // two-row kernel with a 2- or 3-deep halo ring
   static const int sel = getenv("LNX_DWCONV_KERNEL") ? atoi(getenv("LNX_DWCONV_KERNEL")) : 4;
-  if (sel == 4 && H >= 20) {
+  if (sel == 4 && H >= 64) {
     CUtensorMap tmX;
     if (!make_nhwc_tmap(&tmX, x, B, H, W, C, HALO, R4_HALO_H)) return LNX_ERR_UNSUPPORTED;
     const int tiles_h = (H + R4_ROWS - 1) / R4_ROWS;
@@ -422,7 +428,7 @@ int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, co
     }
     const int total = B * tiles_h * tiles_w;
     const int gx = max(1, min(total, (kNumSMs * 2 + chunks - 1) / chunks));
-    dwconv7_fwd_r4_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
+    dwconv7_fwd_r4_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h, wl);
     LNX_CHECK_LAUNCH();
     return LNX_OK;
   }
@@ -441,14 +447,14 @@ int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, const float* bias, co
   const int total = B * tiles_h * tiles_w;
   const int gx = max(1, min(total, (kNumSMs * (ns == 3 ? 2 : 3) + chunks - 1) / chunks));
   if (ns == 3)
-    dwconv7_fwd_x2_kernel<3><<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
+    dwconv7_fwd_x2_kernel<3><<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h, wl);
   else
-    dwconv7_fwd_x2_kernel<2><<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h);
+    dwconv7_fwd_x2_kernel<2><<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, w49c, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h, wl);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
 
-int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, float* dbias, int B, int H, int W, int C, cudaStream_t st) {
+int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, int wl, float* dbias, int B, int H, int W, int C, cudaStream_t st) {
   if (C % CC != 0) return LNX_ERR_SHAPE;
   CUtensorMap tmX, tmG;
   if (!make_nhwc_tmap(&tmX, x, B, H, W, C, HALO, HALO) || !make_nhwc_tmap(&tmG, dy, B, H, W, C, TILE, TILE)) return LNX_ERR_UNSUPPORTED;
@@ -463,7 +469,7 @@ int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, float* d
   const int chunks = C / CC;
   const int total = B * tiles_h * tiles_w;
   const int gx = max(1, min(total, (kNumSMs * 2 + chunks - 1) / chunks));
-  dwconv7_wgrad_x2_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, tmG, dw49c, dbias, B, H, W, C, tiles_w, tiles_h);
+  dwconv7_wgrad_x2_kernel<<<dim3(gx, chunks), NTHREADS, smem, st>>>(tmX, tmG, dw49c, dbias, B, H, W, C, tiles_w, tiles_h, wl);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }

@@ -401,6 +401,58 @@ extern "C" int lnx_rowscale(const void* x, const float* s, void* out, int64_t M,
   return LNX_OK;
 }
 
+// ---------------------------------------------------------------- layer scale (ConvNeXt gamma) plumbing of the pointwise pair
+// w_eff[n, :] = bf16(w[n, :] * cs[n]): the weight the data-gradient kernel sees (gamma folded in), one launch instead of mul + cast
+__global__ void rowscale_cast_kernel(const float* __restrict__ w, const float* __restrict__ cs, bf16* __restrict__ out, int N, int K) {
+  const long long total = (long long)N * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(w[i] * cs[i / K]);
+}
+
+extern "C" int lnx_rowscale_cast_bf16(const float* w, const float* cs, void* out, int N, int K, lnx_stream_t st) {
+  LNX_REQUIRE(w && cs && out, LNX_ERR_NULL);
+  LNX_REQUIRE(N > 0 && K > 0, LNX_ERR_SHAPE);
+  const long long total = (long long)N * K;
+  rowscale_cast_kernel<<<(int)min((long long)kNumSMs * 4, (total + 255) / 256), 256, 0, (cudaStream_t)st>>>(w, cs, (bf16*)out, N, K);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
+// From the UN-scaled gradients of y = cs * (h W2^T + b2):  dW2 += cs dW2_raw,  db2 += cs db2_raw,
+// dcs += rowsum(dW2_raw * W2) + b2 db2_raw  (no pass over activations: SURVEY 8(a4), convnext.py:84).  One block per output row.
+__global__ void layerscale_bwd_kernel(const float* __restrict__ dw_raw, const float* __restrict__ db_raw, const float* __restrict__ w,
+                                      const float* __restrict__ b, const float* __restrict__ cs, float* __restrict__ dw,
+                                      float* __restrict__ db, float* __restrict__ dcs, int K) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const float c = cs[n];
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float g = dw_raw[(long long)n * K + k];
+    acc = fmaf(g, w[(long long)n * K + k], acc);
+    dw[(long long)n * K + k] += g * c;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    const float gb = db_raw ? db_raw[n] : 0.f;
+    if (db) db[n] += gb * c;
+    dcs[n] += t + (b ? b[n] : 0.f) * gb;
+  }
+}
+
+extern "C" int lnx_layerscale_bwd(const float* dw_raw, const float* db_raw, const float* w, const float* b, const float* cs, float* dw,
+                                  float* db, float* dcs, int N, int K, lnx_stream_t st) {
+  LNX_REQUIRE(dw_raw && w && cs && dw && dcs, LNX_ERR_NULL);
+  LNX_REQUIRE(N > 0 && K > 0, LNX_ERR_SHAPE);
+  layerscale_bwd_kernel<<<N, 128, 0, (cudaStream_t)st>>>(dw_raw, db_raw, w, b, cs, dw, db, dcs, K);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
 // ---------------------------------------------------------------- activation backward
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ out, long long n, int act) {

@@ -23,8 +23,13 @@ class FlatGroup:
         dev = self.params[0].device
         self.offsets, off = [], 0
         for p in self.params:
+            # every tensor stays 16-byte aligned - and so does its bf16 shadow for matrices (8-element granularity): the tcgen05 GEMMs
+            # take 16-byte aligned operands only (a [1,2,1] aggregate weight would otherwise push every later matrix onto the slow path)
+            a = 8 if p.ndim >= 2 else 4
+            off = (off + a - 1) // a * a
             self.offsets.append(off)
-            off += (p.numel() + 3) // 4 * 4  # every tensor stays 16-byte aligned
+            off += p.numel()
+        off = (off + 7) // 8 * 8
         self.numel = off
         self.p = torch.zeros(off, dtype=torch.float32, device=dev)
         self.g = torch.zeros(off, dtype=torch.float32, device=dev)

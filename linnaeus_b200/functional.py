@@ -287,7 +287,11 @@ class _Mlp2(torch.autograd.Function):
             dy2 = rowscale(dy2, row_scale, ctx.rpg)
         if col_scale is not None:
             # fold the layer scale into the weight seen by the data-gradient GEMM
-            w2_eff = compute_copy(w2.detach() * col_scale.detach()[:, None], dy2.dtype)
+            if dy2.dtype == torch.bfloat16 and w2.is_contiguous():
+                w2_eff = torch.empty(w2.shape, dtype=torch.bfloat16, device=w2.device)
+                call("lnx_rowscale_cast_bf16", w2.data_ptr(), col_scale.data_ptr(), w2_eff.data_ptr(), N, Hd)
+            else:
+                w2_eff = compute_copy(w2.detach() * col_scale.detach()[:, None], dy2.dtype)
         else:
             w2_eff = w2c
         # dPre = (dy W2_eff) * act'(pre)   [M, Hd]
@@ -301,20 +305,27 @@ class _Mlp2(torch.autograd.Function):
             dpre = gemm(dy2, w2_eff, M, Hd, N, b_trans=True, ldb=Hd, act=ACT_MUL if ctx.save_dg else act, act_grad_in=pre)
         d_cs = dw2 = db2 = None
         if col_scale is not None:
-            db2_raw = torch.zeros(N, dtype=torch.float32, device=dy2.device)
-            dw2_raw = wgrad(dy2, h, db_out=db2_raw)
+            raw = torch.zeros(N * Hd + N, dtype=torch.float32, device=dy2.device)  # one fill: dW2_raw | db2_raw
+            dw2_raw, db2_raw = raw[:N * Hd].view(N, Hd), raw[N * Hd:]
+            wgrad(dy2, h, out=dw2_raw, db_out=db2_raw)
             cs = col_scale.detach()
-            d_cs = (dw2_raw * w2.detach()).sum(1) + b2.detach() * db2_raw
-            if s_w2 is not None:
-                s_w2.view(N, Hd).addcmul_(dw2_raw, cs[:, None])
-                s_b2.addcmul_(db2_raw, cs)
-            else:
-                dw2, db2 = dw2_raw * cs[:, None], db2_raw * cs
             s_cs = _sink(p_cs)
-            if s_cs is not None:
-                s_cs.add_(d_cs)
+            if s_w2 is not None and s_b2 is not None and s_cs is not None and w2.is_contiguous():
+                # one launch: dW2 += cs dW2_raw, db2 += cs db2_raw, dgamma += rowsum(dW2_raw * W2) + b2 db2_raw
+                call("lnx_layerscale_bwd", dw2_raw.data_ptr(), db2_raw.data_ptr(), w2.data_ptr(), b2.data_ptr(), cs.data_ptr(),
+                     s_w2.data_ptr(), s_b2.data_ptr(), s_cs.data_ptr(), N, Hd)
                 _grad_done(p_cs)
-                d_cs = None
+            else:
+                d_cs = (dw2_raw * w2.detach()).sum(1) + b2.detach() * db2_raw
+                if s_w2 is not None:
+                    s_w2.view(N, Hd).addcmul_(dw2_raw, cs[:, None])
+                    s_b2.addcmul_(db2_raw, cs)
+                else:
+                    dw2, db2 = dw2_raw * cs[:, None], db2_raw * cs
+                if s_cs is not None:
+                    s_cs.add_(d_cs)
+                    _grad_done(p_cs)
+                    d_cs = None
         elif s_w2 is not None:
             wgrad(dy2, h, out=s_w2.view(N, Hd), db_out=s_b2)
         else:
@@ -393,19 +404,24 @@ def layernorm_fork(x, w, b, eps=1e-5):
 
 
 # --------------------------------------------------------------------------- depthwise 7x7
+W_TAP_MAJOR, W_NATIVE, W_NATIVE_FLIPPED = 0, 1, 2  # LNX_DW_W_*
+
+
 class _DwConv7(torch.autograd.Function):
     """Depthwise 7x7.  With ``fork`` the input is also returned as a second output (the skip connection of the
     ConvNeXt block): its gradient is then added inside the data-gradient kernel instead of by a separate
-    autograd add over the whole activation."""
+    autograd add over the whole activation.  The kernels read the Conv2d weight [C,1,7,7] in place (the data gradient
+    reads it with the taps reversed) and the weight-gradient kernel accumulates in that layout straight into the
+    parameter's gradient buffer: no transposed / flipped copies, no zero-fill + add launches."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, fork):
         B, H, W, C = x.shape
         x = _c(x)
-        w49c = weight.detach().reshape(C, 49).t().contiguous()
+        w = _c(weight.detach())
         y = torch.empty_like(x)
-        call("lnx_dwconv7_fwd", x.data_ptr(), w49c.data_ptr(), ptr(bias), None, y.data_ptr(), B, H, W, C, dt(x))
-        ctx.save_for_backward(x, w49c)
+        call("lnx_dwconv7_fwd", x.data_ptr(), w.data_ptr(), W_NATIVE, ptr(bias), None, y.data_ptr(), B, H, W, C, dt(x))
+        ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.params = (weight, bias)
         if fork:
@@ -414,19 +430,27 @@ class _DwConv7(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, dskip=None):
-        x, w49c = ctx.saved_tensors
+        x, w = ctx.saved_tensors
         B, H, W, C = x.shape
         dy = _c(dy)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            wflip = w49c.flip(0).contiguous()
             res = _c(dskip) if dskip is not None else None
-            call("lnx_dwconv7_fwd", dy.data_ptr(), wflip.data_ptr(), None, ptr(res), dx.data_ptr(), B, H, W, C, dt(x))
-        dw49c = torch.zeros_like(w49c)
-        db = torch.zeros(C, dtype=torch.float32, device=x.device)
-        call("lnx_dwconv7_wgrad", x.data_ptr(), dy.data_ptr(), dw49c.data_ptr(), db.data_ptr(), B, H, W, C, dt(x))
-        return dx, dw49c.t().reshape(C, 1, 7, 7), (db if ctx.has_bias else None), None
+            call("lnx_dwconv7_fwd", dy.data_ptr(), w.data_ptr(), W_NATIVE_FLIPPED, None, ptr(res), dx.data_ptr(), B, H, W, C, dt(x))
+        p_w, p_b = ctx.params
+        s_w = _sink(p_w)
+        s_b = _sink(p_b) if p_b is not None else None
+        direct = s_w is not None and (p_b is None or s_b is not None)
+        dw = s_w if direct else torch.zeros((C, 1, 7, 7), dtype=torch.float32, device=x.device)
+        db = s_b if direct else torch.zeros(C, dtype=torch.float32, device=x.device)
+        call("lnx_dwconv7_wgrad", x.data_ptr(), dy.data_ptr(), dw.data_ptr(), W_NATIVE, ptr(db), B, H, W, C, dt(x))
+        if direct:
+            _grad_done(p_w)
+            if p_b is not None:
+                _grad_done(p_b)
+            return dx, None, None, None
+        return dx, dw, (db if ctx.has_bias else None), None
 
 
 def dwconv7(x_nhwc, weight, bias):
@@ -559,6 +583,7 @@ class _RopeAttention(torch.autograd.Function):
         call("lnx_attn_fwd", qkv_h[0].data_ptr(), qkv_h[1].data_ptr(), qkv_h[2].data_ptr(), out.data_ptr(), lse.data_ptr(),
              B, heads, N, hd, dt(qkv), int(FORCE_SIMT))
         ctx.save_for_backward(qkv, qkv_h, out, lse, cos, sin)
+        ctx.freqs_param = freqs
         ctx.dims = (B, N, D, heads, hd, half, H, W, n_extra, scale, freqs.shape)
         return out
 
@@ -576,8 +601,12 @@ class _RopeAttention(torch.autograd.Function):
         dtheta = torch.zeros((H * W, heads, half), dtype=torch.float32, device=dev)
         call("lnx_rope_qk_bwd", dqkv_h[0].data_ptr(), dqkv_h[1].data_ptr(), dqkv_h[2].data_ptr(), qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(),
              dqkv.data_ptr(), dtheta.data_ptr(), B, N, heads, hd, n_extra, scale, dt(qkv))
-        dfreqs = torch.zeros(fshape, dtype=torch.float32, device=dev)
-        call("lnx_rope_freq_grad", dtheta.data_ptr(), dfreqs.data_ptr(), H, W, heads, half)
+        s_f = _sink(ctx.freqs_param)
+        dfreqs = s_f if s_f is not None else torch.zeros(fshape, dtype=torch.float32, device=dev)
+        call("lnx_rope_freq_grad", dtheta.data_ptr(), dfreqs.data_ptr(), H, W, heads, half)  # dfreqs +=
+        if s_f is not None:
+            _grad_done(ctx.freqs_param)
+            dfreqs = None
         return dqkv, dfreqs, None, None, None, None
 
 

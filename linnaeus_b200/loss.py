@@ -125,6 +125,49 @@ _KIND_BY_NAME = {
 }
 
 
+class _LazyRowMeans(dict):
+    """``{task: mean of row k of a [K, B] device tensor}`` evaluated on first access: the reference computes these for its log line
+    (hierarchical_loss.py:361-372); computing them eagerly costs 2 K tiny reductions in every training step."""
+
+    def __init__(self, mat: torch.Tensor, keys: list[str]):
+        super().__init__()
+        self._mat, self._keys = mat, list(keys)
+
+    def _fill(self):
+        if self._mat is not None:
+            m = self._mat.mean(dim=1)
+            for i, k in enumerate(self._keys):
+                dict.__setitem__(self, k, m[i])
+            self._mat = None
+
+    def __getitem__(self, k):
+        self._fill()
+        return dict.__getitem__(self, k)
+
+    def __iter__(self):
+        return iter(self._keys)
+
+    def __len__(self):
+        return len(self._keys)
+
+    def __contains__(self, k):
+        return k in self._keys
+
+    def keys(self):
+        return list(self._keys)
+
+    def items(self):
+        self._fill()
+        return dict.items(self)
+
+    def values(self):
+        self._fill()
+        return dict.values(self)
+
+    def get(self, k, default=None):
+        return self[k] if k in self._keys else default
+
+
 def _hard(t: torch.Tensor) -> torch.Tensor:
     return t.argmax(dim=1) if t.dim() == 2 else t.long()
 
@@ -299,8 +342,8 @@ def weighted_hierarchical_loss(
     per = stats["per_sample"]
     loss_components = {
         "total": total.detach(),
-        "tasks": {k: raw[i].mean() for i, k in enumerate(keys)},
-        "masked_tasks": {k: per[i].mean() for i, k in enumerate(keys)},
+        "tasks": _LazyRowMeans(raw, keys),          # per-task means, reduced only when somebody reads them (logging)
+        "masked_tasks": _LazyRowMeans(per, keys),
         "weighted_tasks": {k: stats["task_sum"][i] for i, k in enumerate(keys)},
         "raw_per_sample_losses": {k: raw[i] for i, k in enumerate(keys)},
         "null_masking": {

@@ -95,6 +95,72 @@ class _Bf16Shadow:
         return self.views
 
 
+class _ParamViews:
+    """Cached ``nn.Parameter`` views over one or several model parameters that sit back to back in one storage (after FlatAdamW has
+    re-homed them they do): the stem conv weight as a [Cout, Cin*16] matrix, all K head weights as ONE [sum C_k, D] matrix.  The
+    view's ``.grad`` is the matching view of the members' gradient buffer, so the Linear kernels accumulate weight gradients in
+    place and report per member to a data-parallel wrapper; no torch.cat / pad / reshape copies forward, no CatBackward + K
+    accumulate launches backward.  Returns None when the members are not contiguous (fresh model, no flat optimizer yet)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, tag: str, members: list, shape: tuple):
+        g0 = members[0].grad
+        key = tuple(m.data_ptr() for m in members) + (None if g0 is None else g0.data_ptr(),)
+        hit = self._cache.get(tag)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        view = self._build(members, shape)
+        self._cache[tag] = (key, view)
+        return view
+
+    @staticmethod
+    def _contiguous(ts) -> bool:
+        st = ts[0].untyped_storage().data_ptr()
+        off = ts[0].storage_offset()
+        for t in ts:
+            if t is None or not t.is_contiguous() or t.dtype != torch.float32 or t.untyped_storage().data_ptr() != st or t.storage_offset() != off:
+                return False
+            off += t.numel()
+        return True
+
+    def _build(self, members, shape):
+        n = 1
+        for d in shape:
+            n *= d
+        if sum(m.numel() for m in members) != n or not self._contiguous([m.data for m in members]):
+            return None
+        grads = [m.grad for m in members]
+        if any(g is None for g in grads) or not self._contiguous(grads):
+            return None
+        data = torch.empty(0, dtype=torch.float32, device=members[0].device).set_(members[0].data.untyped_storage(), members[0].storage_offset(), shape)
+        view = nn.Parameter(data, requires_grad=True)
+        view.grad = torch.empty(0, dtype=torch.float32, device=members[0].device).set_(grads[0].untyped_storage(), grads[0].storage_offset(), shape)
+        mem = list(members)
+
+        def ready(_p, mem=mem):
+            for m in mem:  # forward "gradient final" to whoever listens on the real parameters (linnaeus_b200.DataParallel)
+                h = getattr(m, "_lnx_grad_ready", None)
+                if h is not None:
+                    h(m)
+
+        view._lnx_grad_ready = ready
+        view._lnx_members = mem
+        return view
+
+
+def _shadow_view(members: list, shape: tuple, views: dict | None = None):
+    """bf16 shadow of a _ParamViews view: the shadow buffer mirrors the parameter storage element for element."""
+    views = _ACTIVE_SHADOW if views is None else views
+    if views is None:
+        return None
+    first = views.get(id(members[0]))
+    if first is None:
+        return None
+    return torch.empty(0, dtype=first.dtype, device=first.device).set_(first.untyped_storage(), first.storage_offset(), shape)
+
+
 def drop_path_mask(B: int, drop_prob: float, training: bool, device) -> torch.Tensor | None:
     """Per-sample stochastic-depth multiplier floor(keep + U[0,1)) / keep (drop_path.py:11-36); None when inactive.
     The multiplier is applied inside the epilogue of the GEMM that closes the residual branch."""
@@ -340,6 +406,7 @@ class mFormerV1(nn.Module):
         self._compute_dtype: torch.dtype | None = None  # None: follow autocast (on -> bf16, off -> fp32)
         self._shadow: _Bf16Shadow | None = None
         self._side_stream = None  # metadata-token branch (see _extras_async)
+        self._views = _ParamViews()
 
     # -- init / metadata properties (mFormerV1.py:351-405) ---------------------
     def _init_weights(self, m):
@@ -445,11 +512,17 @@ class mFormerV1(nn.Module):
         dims = self.dims
         ex1, ex2, side = self._extras_async(meta, cd)
         # stem: 4x4/s4 conv as im2col (K = 48 padded to 64) + GEMM, then LN (NHWC rows)
-        kpad = ((Cin * 16 + 63) // 64) * 64
+        kpad = ((Cin * 16 + 7) // 8) * 8  # K = 48: the GEMM's TMA box zero-fills the tail of its 64-wide k-block
         a = F.patchify(x, 4, kpad, cd)
         conv = self.stem[0]
-        w2d = TF.pad(conv.weight.reshape(dims[0], Cin * 16), (0, kpad - Cin * 16))
-        y = F.linear(a, w2d, conv.bias)
+        w2d = self._views.get("stem", [conv.weight], (dims[0], Cin * 16)) if kpad == Cin * 16 and torch.is_grad_enabled() else None
+        if w2d is not None:
+            y = F.linear(a, w2d, conv.bias, weight_c=_shadow_view([conv.weight], (dims[0], Cin * 16)))
+        else:
+            w2d = conv.weight.reshape(dims[0], Cin * 16)
+            if kpad != Cin * 16:
+                w2d = TF.pad(w2d, (0, kpad - Cin * 16))
+            y = F.linear(a, w2d, conv.bias)
         y = F.layernorm(y, self.stem[1].weight, self.stem[1].bias, 1e-6)
         H, W = Hi // 4, Wi // 4
         for blk in self.stages[0]:
@@ -500,16 +573,27 @@ class mFormerV1(nn.Module):
             for t, head in self.head.items():
                 w, b = head.classifier_params()
                 ws.append(w)
-                bs.append(b if b is not None else torch.zeros(w.shape[0], device=w.device))
+                bs.append(b)
                 offs.append(offs[-1] + w.shape[0])
-            wcat = torch.cat(ws, 0)
-            bcat = torch.cat(bs, 0)
             # pad the class dimension to a multiple of 8 so the tensor-core epilogue stays vectorised
             pad = (-offs[-1]) % 8
-            if pad:
-                wcat = TF.pad(wcat, (0, 0, 0, pad))
-                bcat = TF.pad(bcat, (0, pad))
-            cat = F.linear(feats, wcat, bcat, out_dtype=torch.float32)
+            wcat = bcat = wcat_c = None
+            if not pad and all(b is not None for b in bs) and torch.is_grad_enabled():
+                # the K classifiers as one matrix without copying (contiguous once the flat optimizer owns the parameters)
+                wcat = self._views.get("head_w", ws, (offs[-1], ws[0].shape[1]))
+                bcat = self._views.get("head_b", bs, (offs[-1],)) if wcat is not None else None
+                if bcat is None:
+                    wcat = None
+                else:
+                    wcat_c = (_shadow_view(ws, (offs[-1], ws[0].shape[1]), self._shadow.views)
+                              if feats.dtype == torch.bfloat16 and self._shadow is not None else None)
+            if wcat is None:
+                wcat = torch.cat(ws, 0)
+                bcat = torch.cat([b if b is not None else torch.zeros(w.shape[0], device=w.device) for w, b in zip(ws, bs)], 0)
+                if pad:
+                    wcat = TF.pad(wcat, (0, 0, 0, pad))
+                    bcat = TF.pad(bcat, (0, pad))
+            cat = F.linear(feats, wcat, bcat, weight_c=wcat_c, out_dtype=torch.float32)
             out = LogitsDict()
             for i, t in enumerate(self.head.keys()):
                 out[t] = cat[:, offs[i]:offs[i + 1]]

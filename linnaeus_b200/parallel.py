@@ -43,7 +43,7 @@ def plan_buckets(groups: list[FlatGroup], bucket_bytes: int) -> tuple[list[_Buck
         lo, count = 0, 0
         for i, p in enumerate(g.params):
             a, b = g.span(i)
-            end = (b + 3) // 4 * 4
+            end = g.offsets[i + 1] if i + 1 < len(g.params) else g.numel  # next tensor's (aligned) start
             count += 1
             owner[id(p)] = len(buckets)
             last = i == len(g.params) - 1

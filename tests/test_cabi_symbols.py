@@ -70,7 +70,7 @@ def test_argument_validation_needs_no_gpu(lib):
     buf = (ctypes.c_float * 64)()
     p = ctypes.addressof(buf)
     assert lib.lnx_layernorm_fwd(p, p, p, None, p, None, None, 0, 32, 1e-5, 0, None) == -1  # rows == 0
-    assert lib.lnx_dwconv7_fwd(p, p, None, None, p, 1, 8, 8, 33, 0, None) == -1  # C % 32 != 0
+    assert lib.lnx_dwconv7_fwd(p, p, 0, None, None, p, 1, 8, 8, 33, 0, None) == -1  # C % 32 != 0
     assert lib.lnx_layernorm_fwd(p, p, p, None, p, None, None, 1, 32, 1e-5, 7, None) == -2  # bad dtype
 
 

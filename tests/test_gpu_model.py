@@ -254,7 +254,8 @@ def test_inference_weight_cache_never_goes_stale():
     model.train()
     ts.step(x, meta, tg)  # eager optimizer step
     a1 = infer()
-    assert not torch.equal(a1, a0) and torch.equal(a1, fresh())
+    same = lambda u, v: torch.allclose(u, v, rtol=0, atol=1e-5)  # noqa: E731  (grad-enabled forwards read the K head weights through one view of the flat buffer: same values, possibly another GEMM tiling; a stale cache is off by ~1e-1)
+    assert not torch.equal(a1, a0) and same(a1, fresh())
     model.train()
     ts.capture(x, meta, tg)
     b0 = infer()
@@ -262,13 +263,13 @@ def test_inference_weight_cache_never_goes_stale():
     ts.replay()  # the optimizer runs inside the graph
     torch.cuda.synchronize()
     b1 = infer()
-    assert not torch.equal(b1, b0) and torch.equal(b1, fresh())
+    assert not torch.equal(b1, b0) and same(b1, fresh())
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     with torch.no_grad():
         for p in model.parameters():
             p.mul_(1.5)
     c0 = infer()
-    assert torch.equal(c0, fresh())
+    assert same(c0, fresh())
     model.load_state_dict(sd)
     assert torch.equal(infer(), b1)
 

@@ -36,19 +36,19 @@ for B, H, C in ((256, 56, 96), (256, 28, 192), (32, 96, 256)):
     w49 = w.reshape(C, 49).t().contiguous()
     bias = 0.1 * torch.randn(C, device=DEV)
     y = torch.empty_like(x)
-    _lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), bias.data_ptr(), None, y.data_ptr(), B, H, H, C, 1)
+    _lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), 0, bias.data_ptr(), None, y.data_ptr(), B, H, H, C, 1)
     ref = TF.conv2d(x.float().permute(0, 3, 1, 2), w, bias, padding=3, groups=C).permute(0, 2, 3, 1)
     err = float((y.float() - ref).abs().max() / ref.abs().max())
-    t_f = timeit(lambda: _lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), bias.data_ptr(), None, y.data_ptr(), B, H, H, C, 1))
-    t_d = timeit(lambda: _lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), None, g.data_ptr(), y.data_ptr(), B, H, H, C, 1))
+    t_f = timeit(lambda: _lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), 0, bias.data_ptr(), None, y.data_ptr(), B, H, H, C, 1))
+    t_d = timeit(lambda: _lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), 0, None, g.data_ptr(), y.data_ptr(), B, H, H, C, 1))
     dw = torch.zeros(49, C, device=DEV)
     db = torch.zeros(C, device=DEV)
-    _lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H, H, C, 1)
+    _lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), 0, db.data_ptr(), B, H, H, C, 1)
     xr = x.float().permute(0, 3, 1, 2).contiguous()
     wr = w.clone().requires_grad_(True)
     TF.conv2d(xr, wr, None, padding=3, groups=C).backward(g.float().permute(0, 3, 1, 2))
     werr = float((dw.t().reshape(C, 1, 7, 7) - wr.grad).norm() / wr.grad.norm())
-    t_w = timeit(lambda: _lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H, H, C, 1))
+    t_w = timeit(lambda: _lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), 0, db.data_ptr(), B, H, H, C, 1))
     fl = 2.0 * 49 * B * H * H * C
     print(f"{B}x{H}x{H}x{C}: fwd {t_f:.4f} ms ({fl / t_f / 1e9:.1f} TFLOP/s, err {err:.1e}) | dgrad+skip {t_d:.4f} ms | wgrad {t_w:.4f} ms "
           f"({fl / t_w / 1e9:.1f} TFLOP/s, relL2 {werr:.1e})", flush=True)

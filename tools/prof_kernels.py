@@ -88,8 +88,8 @@ bc = torch.randn(C, device=dev)
 dw49 = torch.zeros(49, C, device=dev)
 dbc = torch.zeros(C, device=dev)
 nb = xi.numel() * 2
-bench("dwconv7 fwd                        256x56x56x96", lambda: call("lnx_dwconv7_fwd", xi.data_ptr(), w49.data_ptr(), bc.data_ptr(), None, yo.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
-bench("dwconv7 wgrad                      256x56x56x96", lambda: call("lnx_dwconv7_wgrad", xi.data_ptr(), gi.data_ptr(), dw49.data_ptr(), dbc.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
+bench("dwconv7 fwd                        256x56x56x96", lambda: call("lnx_dwconv7_fwd", xi.data_ptr(), w49.data_ptr(), 0, bc.data_ptr(), None, yo.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
+bench("dwconv7 wgrad                      256x56x56x96", lambda: call("lnx_dwconv7_wgrad", xi.data_ptr(), gi.data_ptr(), dw49.data_ptr(), 0, dbc.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
 x2 = xi.view(-1, C)
 g2 = gi.view(-1, C)
 y2d = yo.view(-1, C)

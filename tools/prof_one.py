@@ -20,9 +20,9 @@ dw = torch.zeros(49, C, device=DEV)
 db = torch.zeros(C, device=DEV)
 for _ in range(4):
     if what == "dwconv_fwd":
-        _lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), bias.data_ptr(), None, y.data_ptr(), B, H, H, C, 1)
+        _lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), 0, bias.data_ptr(), None, y.data_ptr(), B, H, H, C, 1)
     elif what == "dwconv_wgrad":
-        _lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), db.data_ptr(), B, H, H, C, 1)
+        _lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), 0, db.data_ptr(), B, H, H, C, 1)
     elif what == "mlp_bwd":
         M = B * H * H
         w1 = (torch.randn(4 * C, C, device=DEV) * C ** -0.5).to(torch.bfloat16)
