@@ -130,6 +130,13 @@ int lnx_mlp_fused_fwd(const void* x, const void* w1, const float* b1, const void
  * Replaces autograd through R/models/blocks/convnext.py:79-86. */
 int lnx_mlp_fused_bwd(const void* x, const void* dy, const void* w1, const float* b1, const void* w2e, void* h, void* dpre, void* dx,
                       int64_t M, int C, int H, lnx_stream_t s);
+/* The weight gradients of the same pair without any 4C-wide tensor in HBM (pass h = dpre = NULL to lnx_mlp_fused_bwd then):
+ * every CTA owns one third of the hidden units, recomputes its slice of the pre-activation and of dY W2e per row tile, and
+ * accumulates dw1[H,C] += dpre^T x and dw2_raw[C,H] += dy^T h in TMEM across all its row tiles (one atomic flush at the end);
+ * db1[H] += colsum(dpre) (extra MMA columns against a tile of ones).  "raw" = before the layer scale (lnx_layerscale_bwd finishes
+ * it; db2_raw = lnx_colsum(dy)).  C = 96. */
+int lnx_mlp_fused_wgrad(const void* x, const void* dy, const void* w1, const float* b1, const void* w2e, float* dw1, float* db1,
+                        float* dw2_raw, int64_t M, int C, int H, lnx_stream_t s);
 
 /* acc[m,n] = sum_k A(m,k) * B(n,k)
  *   a_trans = 0: A stored [M,K] (row pitch lda); 1: stored [K,M]

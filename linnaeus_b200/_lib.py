@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "liblinnaeus_b200.so")
+LIB_PATH = os.environ.get("LNX_LIB_PATH") or os.path.join(_PKG, "liblinnaeus_b200.so")  # override: profiling builds (tools/build_variant.sh)
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_DG, ACT_MUL, ACT_SWISH = 0, 1, 2, 3, 4, 5
@@ -44,6 +44,7 @@ SIGNATURES = {
     "lnx_wgrad": [P, L, P, L, P, P, L, I, I, I, P],
     "lnx_mlp_fused_fwd": [P, P, P, P, P, P, P, I, P, P, L, I, I, P],
     "lnx_mlp_fused_bwd": [P, P, P, P, P, P, P, P, L, I, I, P],
+    "lnx_mlp_fused_wgrad": [P, P, P, P, P, P, P, P, L, I, I, P],
     "lnx_im2col3x3": [P, I, P, I, I, I, I, I, I, I, I, I, P],
     "lnx_conv3x3_s1": [P, P, P, P, I, I, I, I, I, I, I, P],
     "lnx_maxpool3s2": [P, P, I, I, I, I, I, P],

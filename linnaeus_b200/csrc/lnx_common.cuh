@@ -200,9 +200,11 @@ __device__ __forceinline__ void gelu_both_tanh3_x2(float2 x, float2& gl, float2&
 
 // Leanest erf-GELU for the fused pointwise-pair kernels, where the GELU warps are the critical resource: cubic argument
 // x (q0 + q1 x^2) (monotone, so no clamp; max |GELU error| 2.7e-4 before the bf16 rounding of the hidden tile, rms error
-// after rounding 1.703e-3 against 1.694e-3 for exact erf-GELU) and one MUFU.TANH per element.  Measured on B200:
-// MUFU.TANH issues at HALF the MUFU rate (8 / clk / SM), which is what bounds these kernels (2048 cycles per 128 x 128 chunk);
-// tanh.approx.f16x2 compiles to two MUFU.TANH.F16, so packing buys nothing.  gelu2q returns 2 gelu(x): the caller folds the
+// after rounding 1.703e-3 against 1.694e-3 for exact erf-GELU) and one MUFU.TANH per element.  Measured on B200
+// (tools/microbench): every MUFU op issues at 16 / clk / SM, FFMA2 at the same FMA rate as FFMA (124 FMA / clk / SM), and this
+// body alone (bias add + gelu + pack, registers only) runs at 12.6 elements / clk / SM from 8 warps (1300 cycles per 128 x 128
+// chunk); with the derivative it is FMA-pipe bound at 8.5 elements / clk / SM.  tanh.approx.f16x2 compiles to two MUFU.TANH.F16,
+// so packing buys nothing.  gelu2q returns 2 gelu(x): the caller folds the
 // 0.5 into the next scale.  gelu2q_both also returns the derivative of the same approximation (backward recompute).
 constexpr float kGeluQ0 = 0.80015625f, kGeluQ1 = 0.034701171875f;
 __device__ __forceinline__ float2 gelu2q_x2(float2 x) {  // 2 gelu(x)

@@ -24,6 +24,12 @@ using namespace lnx_mlp;
 
 namespace {
 
+// Ablation switches for profiling builds (tools/build_variant.sh -DLNX_DBG=n; the shipped library is built with 0, results are wrong
+// otherwise): 1 bias from a constant, 4 no GELU math (raw accumulator bits packed), 16 no MMA1, 32 no MMA2.
+#ifndef LNX_DBG
+#define LNX_DBG 0
+#endif
+
 struct FusedArgs {
   const float* b1;
   const float* b2;
@@ -211,13 +217,14 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1)
           }
           const uint32_t xa = smem_u32(xs) + s * CF::X_BYTES;
           const uint32_t tpre = tmem_base + (g % NPRE) * HC;
+          if (!(LNX_DBG & 16))
 #pragma unroll
           for (int kb = 0; kb < KB64; ++kb)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tpre, desc_k128(xa + kb * (BM * 128) + k * 32), desc_k128(w1c + kb * CF::W1_KB_STRIDE + k * 32), idesc1,
                         (kb > 0 || k > 0) ? 1u : 0u);
-          if (KREM) {
+          if (KREM && !(LNX_DBG & 16)) {
             // the 32-wide remainder block: [rows][64 B], 64-byte swizzle; chunk j starts j * HC * 64 bytes into the resident block
             const uint32_t w1r = RESIDENT ? smem_u32(w1s) + KB64 * CF::W1_KB_STRIDE + j * HC * 64 : w1c + KB64 * CF::W1_KB_STRIDE;
 #pragma unroll
@@ -250,6 +257,7 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1)
           }
           const uint32_t th = tmem_base + (gp % NPRE) * HC;
           const uint32_t ty = tmem_base + Y_COL0 + ys * C;
+          if (!(LNX_DBG & 32))
 #pragma unroll
           for (int kk = 0; kk < HC / 16; ++kk)
             umma_bf16_ts(ty, th + 32 * (kk >> 1) + 8 * (kk & 1), desc_k128(w2c + (kk >> 2) * (C * 128) + (kk & 3) * 32), idesc2,
@@ -334,20 +342,29 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1)
       mbar_wait(&pre_full[b], (g / NPRE) & 1u);
       tcgen05_fence_after();
       const uint32_t tbuf = tmem_base + b * HC + lane_off;
+      // the TMEM read of the next 32-column block is in flight while this one is computed (its ~100-cycle latency is otherwise exposed)
+      constexpr int NBLK = CF::CPS / 32;
+      uint32_t acc[NBLK > 1 ? 2 : 1][32];
+      tmem_ld32_nowait(tbuf + slice * CF::CPS, acc[0]);
 #pragma unroll
-      for (int cb = 0; cb < CF::CPS / 32; ++cb) {
+      for (int cb = 0; cb < NBLK; ++cb) {
         const int col = slice * CF::CPS + cb * 32;
-        uint32_t acc[32];
-        tmem_ld32_nowait(tbuf + col, acc);
         tmem_ld_wait();
+        if (cb + 1 < NBLK) tmem_ld32_nowait(tbuf + col + 32, acc[(cb + 1) & 1]);
+        const uint32_t* ac = acc[cb & 1];
         const float* bp = b1s + j * HC + col;
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          const float4 bv = *reinterpret_cast<const float4*>(bp + 2 * i);
+          if (LNX_DBG & 4) {
+            pk[i] = ac[2 * i] ^ ac[2 * i + 1];
+            pk[i + 1] = ac[2 * i + 2] ^ ac[2 * i + 3];
+            continue;
+          }
+          const float4 bv = (LNX_DBG & 1) ? make_float4(0.1f, 0.2f, 0.3f, 0.4f) : *reinterpret_cast<const float4*>(bp + 2 * i);
           // h holds 2 gelu(pre): the output warps fold the 0.5 into gamma
-          const float2 r0 = gelu2q_x2(__fadd2_rn(make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])), make_float2(bv.x, bv.y)));
-          const float2 r1 = gelu2q_x2(__fadd2_rn(make_float2(__uint_as_float(acc[2 * i + 2]), __uint_as_float(acc[2 * i + 3])), make_float2(bv.z, bv.w)));
+          const float2 r0 = gelu2q_x2(__fadd2_rn(make_float2(__uint_as_float(ac[2 * i]), __uint_as_float(ac[2 * i + 1])), make_float2(bv.x, bv.y)));
+          const float2 r1 = gelu2q_x2(__fadd2_rn(make_float2(__uint_as_float(ac[2 * i + 2]), __uint_as_float(ac[2 * i + 3])), make_float2(bv.z, bv.w)));
           pk[i] = pack_bf16x2(r0.x, r0.y);
           pk[i + 1] = pack_bf16x2(r1.x, r1.y);
         }

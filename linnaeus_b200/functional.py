@@ -218,16 +218,25 @@ def mlp_fused_fwd(x2, w1c, b1, w2c, b2, gamma=None, row_scale=None, rows_per_gro
     return out
 
 
-def mlp_fused_bwd(x2, dy2, w1c, b1, w2e):
-    """-> (h, dpre, dx): recomputes the pre-activation from x, one kernel (see lnx_mlp_fused_bwd)."""
+def mlp_fused_bwd(x2, dy2, w1c, b1, w2e, store_hidden: bool = True):
+    """-> (h, dpre, dx): recomputes the pre-activation from x, one kernel (see lnx_mlp_fused_bwd).  ``store_hidden=False``: only
+    dx is produced (h = dpre = None); the weight gradients then come from :func:`mlp_fused_wgrad`."""
     M, C = x2.shape
     Hd = w1c.shape[0]
-    h = torch.empty((M, Hd), dtype=torch.bfloat16, device=x2.device)
-    dpre = torch.empty((M, Hd), dtype=torch.bfloat16, device=x2.device)
+    h = torch.empty((M, Hd), dtype=torch.bfloat16, device=x2.device) if store_hidden else None
+    dpre = torch.empty((M, Hd), dtype=torch.bfloat16, device=x2.device) if store_hidden else None
     dx = torch.empty((M, C), dtype=torch.bfloat16, device=x2.device)
-    call("lnx_mlp_fused_bwd", x2.data_ptr(), dy2.data_ptr(), w1c.data_ptr(), ptr(b1), w2e.data_ptr(), h.data_ptr(), dpre.data_ptr(),
-         dx.data_ptr(), M, C, Hd)
+    call("lnx_mlp_fused_bwd", x2.data_ptr(), dy2.data_ptr(), w1c.data_ptr(), ptr(b1), w2e.data_ptr(), ptr(h), ptr(dpre), dx.data_ptr(), M, C, Hd)
     return h, dpre, dx
+
+
+def mlp_fused_wgrad(x2, dy2, w1c, b1, w2e, dw1, db1, dw2_raw, db2_raw):
+    """dw1 += dpre^T x, db1 += colsum(dpre), dw2_raw += dy^T h (accumulated on chip, nothing 4C-wide in HBM); db2_raw += colsum(dy)."""
+    M, C = x2.shape
+    call("lnx_mlp_fused_wgrad", x2.data_ptr(), dy2.data_ptr(), w1c.data_ptr(), ptr(b1), w2e.data_ptr(), dw1.data_ptr(), ptr(db1),
+         dw2_raw.data_ptr(), M, C, w1c.shape[0])
+    if db2_raw is not None:
+        colsum(dy2, out=db2_raw)
 
 
 # --------------------------------------------------------------------------- two-layer MLP

@@ -75,6 +75,35 @@ def test_fused_backward_matches_fp32_torch(M):
     assert _rel(dx, dpre_ref.to(torch.bfloat16).float() @ w1.float()) < TOL
 
 
+@pytest.mark.parametrize("M", [1, 128, 300, 4113, 50000, 256 * 56 * 56])
+def test_on_chip_weight_gradients_match_fp32_torch(M):
+    """lnx_mlp_fused_wgrad recomputes h / dPre per row tile and accumulates dW1, db1, dW2 in tensor memory (nothing 4C wide
+    in HBM); lnx_mlp_fused_bwd without the hidden stores is its dX companion.  Both accumulate / compare in relative L2:
+    M-long fp32 sums of bf16-rounded products."""
+    import linnaeus_b200.functional as F
+
+    C, H = 96, 384
+    x, w1, b1, w2, b2, gamma, res, dy = _make(M, C, seed=4)
+    w2e = (w2.float() * gamma[:, None]).to(torch.bfloat16)
+    dw1 = torch.zeros(H, C, device=DEV)
+    db1 = torch.zeros(H, device=DEV)
+    dw2 = torch.zeros(C, H, device=DEV)
+    db2 = torch.zeros(C, device=DEV)
+    F.mlp_fused_wgrad(x, dy, w1, b1, w2e, dw1, db1, dw2, db2)
+    h0, dpre0, dx = F.mlp_fused_bwd(x, dy, w1, b1, w2e, store_hidden=False)
+    assert h0 is None and dpre0 is None
+    pre = x.float() @ w1.float().t() + b1
+    h = TF.gelu(pre).to(torch.bfloat16).float()
+    dpre = ((dy.float() @ w2e.float()) * _gelu_grad(pre)).to(torch.bfloat16).float()
+    del pre
+    for got, ref in ((dw1, dpre.t() @ x.float()), (db1, dpre.sum(0)), (dw2, dy.float().t() @ h), (db2, dy.float().sum(0)),
+                     (dx.float(), dpre @ w1.float())):
+        assert float((got - ref).norm() / ref.norm()) < 5e-3
+    # accumulation: a second call adds the same amounts again
+    F.mlp_fused_wgrad(x, dy, w1, b1, w2e, dw1, db1, dw2, None)
+    assert float((dw1 - 2 * (dpre.t() @ x.float())).norm() / dw1.norm()) < 5e-3
+
+
 def test_fused_kernels_at_the_bench_shape():
     """M = 802 816 rows: 6272 row tiles over 148 persistent CTAs (42 or 43 tiles each), the shape the train step launches."""
     import linnaeus_b200.functional as F

@@ -73,6 +73,28 @@ def check_bwd(M, C=96):
     return max(errs)
 
 
+def check_wgrad(M, C=96):
+    x, w1, b1, w2, b2, gamma, res = make(M, C)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    dy = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    w2e = (w2.float() * gamma[:, None]).to(torch.bfloat16)
+    H = 4 * C
+    dw1 = torch.zeros(H, C, device=DEV)
+    db1 = torch.zeros(H, device=DEV)
+    dw2 = torch.zeros(C, H, device=DEV)
+    db2 = torch.zeros(C, device=DEV)
+    F.mlp_fused_wgrad(x, dy, w1, b1, w2e, dw1, db1, dw2, db2)
+    _, _, dx = F.mlp_fused_bwd(x, dy, w1, b1, w2e, store_hidden=False)
+    torch.cuda.synchronize()
+    pre = x.float() @ w1.float().t() + b1
+    h = TF.gelu(pre).to(torch.bfloat16).float()
+    dpre = ((dy.float() @ w2e.float()) * gelu_grad(pre)).to(torch.bfloat16).float()
+    refs = (dpre.t() @ x.float(), dpre.sum(0), dy.float().t() @ h, dy.float().sum(0), dpre @ w1.float())
+    errs = [float((a - r).norm() / r.norm()) for a, r in zip((dw1, db1, dw2, db2, dx.float()), refs)]
+    print(f"wgrad M={M:7d}: relL2 dW1 {errs[0]:.2e} db1 {errs[1]:.2e} dW2raw {errs[2]:.2e} db2raw {errs[3]:.2e} | dX-only {errs[4]:.2e}", flush=True)
+    return max(errs)
+
+
 def timeit(fn, iters=20, flush=None):
     for _ in range(3):
         fn()
@@ -99,7 +121,22 @@ def bench_only(C, M, iters=5):
     torch.cuda.synchronize()
 
 
+def time_fwd(C):
+    M = 802816 if C == 96 else 200704
+    x, w1, b1, w2, b2, gamma, res = make(M, C)
+    out = torch.empty_like(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    import os
+    if os.environ.get("NORES"):
+        res = None
+    t = timeit(lambda: F.mlp_fused_fwd(x, w1, b1, w2, b2, gamma=gamma, residual=res, out=out), flush=flush)
+    print(f"C={C} M={M} fused fwd {t:.4f} ms", flush=True)
+
+
 def main():
+    if "--time-fwd" in sys.argv:
+        time_fwd(int(sys.argv[sys.argv.index("--time-fwd") + 1]))
+        return
     if "--bench-only" in sys.argv:
         C = int(sys.argv[sys.argv.index("--bench-only") + 1])
         bench_only(C, 802816 if C == 96 else 200704)
@@ -134,6 +171,10 @@ def main():
     for M in (128, 300, 4113, 50000, 802816):
         wb = max(wb, check_bwd(M))
     print("worst bwd rel err", wb)
+    ww = 0.0
+    for M in (128, 300, 4113, 50000, 802816):
+        ww = max(ww, check_wgrad(M))
+    print("worst wgrad relL2", ww)
     M, C = 802816, 96
     x, w1, b1, w2, b2, gamma, res = make(M, C)
     dy = torch.randn(M, C, device=DEV).to(torch.bfloat16)
@@ -146,6 +187,10 @@ def main():
         F.gemm(dpre, w1, M, C, 4 * C, b_trans=True, ldb=C)
 
     t_2b = timeit(two_b, flush=flush)
+    dw1 = torch.zeros(4 * C, C, device=DEV); db1 = torch.zeros(4 * C, device=DEV); dw2 = torch.zeros(C, 4 * C, device=DEV); db2 = torch.zeros(C, device=DEV)
+    t_w = timeit(lambda: F.mlp_fused_wgrad(x, dy, w1, b1, w2e, dw1, db1, dw2, db2), flush=flush)
+    t_dx = timeit(lambda: F.mlp_fused_bwd(x, dy, w1, b1, w2e, store_hidden=False), flush=flush)
+    print(f"on-chip weight gradients {t_w:.4f} ms | dX-only data kernel {t_dx:.4f} ms | sum {t_w + t_dx:.4f} ms (vs data kernel with h / dPre stores + 2 lnx_wgrad)", flush=True)
     print(f"bwd data path C={C} M={M}: fused (recompute; writes h, dpre, dx) {t_b:.4f} ms ({11 * M * C * 2 / t_b / 1e6:.0f} GB/s) | dPre + dX GEMMs {t_2b:.4f} ms",
           flush=True)
 
