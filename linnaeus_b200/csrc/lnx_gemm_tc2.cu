@@ -17,6 +17,8 @@
 // carries only its own instructions: with K = 96 the conv-stage GEMMs are pure epilogue/HBM work.
 // Optional fused column sums of the output (bias gradients) are accumulated per CTA in shared memory across its
 // tiles and flushed with one atomic per column.
+#include <stdlib.h>
+
 #include "lnx_gemm.cuh"
 #include "lnx_tc_common.cuh"
 
@@ -535,6 +537,8 @@ bool tmap2d_32(CUtensorMap* tm, const void* ptr, long long inner, long long oute
 }
 
 int pick_block_n2(int N, bool b_trans) {
+  static const int forced = getenv("LNX_GEMM_BN") ? atoi(getenv("LNX_GEMM_BN")) : 0;  // experiments
+  if (forced && N > 256 && N % forced == 0) return forced;
   if (b_trans) {
     if (N <= 64) return 64;
     if (N <= 128) return 128;

@@ -28,6 +28,8 @@ constexpr int MAX_SMEM = 232448;
 constexpr int BLK_BYTES = BLOCK_K * 128;  // one [32 k][64 mn] swizzled block
 constexpr int ONES_BYTES = BLOCK_K * 128;  // [32 k][64 n] bf16 MN-major block of ones appended to every B stage
 constexpr int DB_COLS = 16;           // extra accumulator columns (column block_n = colsum(dY))
+constexpr int FLUSH_BLK_BYTES = 32 * 128;  // [32 rows][32 float32] staging block of the epilogue flush
+constexpr int FLUSH_BUFS = 2;              // per epilogue warp; 4 warps x 2 x 4 KB = 32 KB <= the smallest operand ring (4 in flight measured no faster)
 
 struct WgParams {
   int M, N, K;          // reduction length, dW rows, dW columns
@@ -44,7 +46,8 @@ template <int COLS>
 __device__ __forceinline__ void alloc_cols(uint32_t* slot) { tmem_alloc<COLS>(slot); }
 
 __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                               float* __restrict__ dw, float* __restrict__ db, const WgParams p) {
+                                                               const __grid_constant__ CUtensorMap tmW, float* __restrict__ dw,
+                                                               float* __restrict__ db, const WgParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int a_bytes = p.mt * BLOCK_M * BLOCK_K * 2;
@@ -135,21 +138,38 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
     mbar_wait(tfull_bar, 0);
     tcgen05_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    // Split-K partials leave as TMA reduce-adds: each warp stages [32 rows][32 columns] float32 blocks (128-byte rows, 128B swizzle)
+    // in the operand ring -- every load has been consumed once tfull_bar fires -- and the L2 adds whole rows; two blocks in flight.
+    // (Per-thread float4 atomics were 13-22 us of every launch: 28 MB of 16-byte L2 operations from 148 CTAs at once.)
+    unsigned char* stg = base + (size_t)(warp - 2) * (FLUSH_BUFS * FLUSH_BLK_BYTES);
+    int nb = 0;
     for (int mt = 0; mt < p.mt; ++mt) {
       const int m = m_base + mt * BLOCK_M + row;
+      const int m_blk = m_base + mt * BLOCK_M + q * 32;  // warp-uniform: first dW row of this warp's block
       for (int nt = 0; nt < p.nt; ++nt) {
         const int n0 = n_base + nt * p.block_n;
-        for (int c = 0; c < p.block_n; c += 16) {
-          if (n0 + c >= p.K) break;  // warp-uniform
-          float v[16];
+        for (int c = 0; c < p.block_n; c += 32) {
+          if (n0 + c >= p.K || m_blk >= p.N) break;  // warp-uniform
+          uint32_t v[32];
           __syncwarp();
-          tmem_ld16(trow + (mt * p.nt + nt) * p.tile_cols + c, v);
-          if (m < p.N) {
-            float* dst = dw + (long long)m * p.K + n0 + c;
-#pragma unroll
-            for (int h = 0; h < 4; ++h)
-              if (n0 + c + h * 4 < p.K) atomicAdd(reinterpret_cast<float4*>(dst + h * 4), make_float4(v[h * 4], v[h * 4 + 1], v[h * 4 + 2], v[h * 4 + 3]));
+          tmem_ld16_nowait(trow + (mt * p.nt + nt) * p.tile_cols + c, v);  // block_n is a multiple of 64
+          tmem_ld16_nowait(trow + (mt * p.nt + nt) * p.tile_cols + c + 16, v + 16);
+          tmem_ld_wait();
+          unsigned char* blk = stg + (nb % FLUSH_BUFS) * FLUSH_BLK_BYTES;
+          if (nb >= FLUSH_BUFS) {
+            if (lane == 0) bulk_wait_group_read<FLUSH_BUFS - 1>();  // the bulk op that last read this buffer is done with it
+            __syncwarp();
           }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(blk + sw128_chunk(lane, j)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmW, blk, n0 + c, m_blk);
+            bulk_commit_group();
+          }
+          ++nb;
         }
       }
       if (do_db) {
@@ -159,6 +179,8 @@ __global__ void __launch_bounds__(NUM_THREADS) wgrad_tc_kernel(const __grid_cons
         if (m < p.N) atomicAdd(db + m, v[0]);
       }
     }
+    if (lane == 0) bulk_wait_group_all();
+    __syncwarp();
   }
 
   tcgen05_fence_before();
@@ -235,15 +257,16 @@ extern "C" int lnx_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx
   splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   const size_t smem = (size_t)p.stages * stage + 4096;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmW;
   if (!tmap_mn(&tmA, dy, N, M, ldy) || !tmap_mn(&tmB, x, K, M, ldx)) return LNX_ERR_UNSUPPORTED;
+  if (!make_tmap_f32(&tmW, dw, K, N, K, 32, 32)) return LNX_ERR_UNSUPPORTED;
   static int smem_set = 0;
   if ((int)smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return lnx_set_cuda_error(e);
     smem_set = (int)smem;
   }
-  wgrad_tc_kernel<<<dim3(ctas_xy, splits), NUM_THREADS, smem, st>>>(tmA, tmB, dw, db, p);
+  wgrad_tc_kernel<<<dim3(ctas_xy, splits), NUM_THREADS, smem, st>>>(tmA, tmB, tmW, dw, db, p);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }

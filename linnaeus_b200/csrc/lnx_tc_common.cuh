@@ -76,6 +76,18 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// global[tile] += smem tile (float32), performed by the L2 on whole 128-byte rows: one bulk operation instead of per-thread atomics;
+// rows / columns outside the tensor map are clipped.  Completion is tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"((uint32_t)__cvta_generic_to_shared(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -185,6 +197,18 @@ inline bool make_tmap(CUtensorMap* tm, const void* ptr, int rank, const long lon
   for (int i = 0; i + 1 < rank; ++i) s[i] = (cuuint64_t)strides_elems[i] * 2;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// float32 tensor map (rank 2, 128B swizzle): the destination of TMA reduce-add flushes of split-K partial sums
+inline bool make_tmap_f32(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld_elems, int box_inner, int box_outer) {
+  auto enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t d[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t s[1] = {(cuuint64_t)ld_elems * 4};
+  cuuint32_t b[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer}, e[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2u, const_cast<void*>(ptr), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
