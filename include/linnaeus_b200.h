@@ -171,6 +171,9 @@ int lnx_rope_qk_fwd(const void* qkv, const float* cos_tab, void* q, void* k, voi
 /* dq,dk,dv [B,heads,N,hd] -> dqkv [B,N,3,heads,hd]; dtheta[N_img,heads,hd/2] += */
 int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, const void* qkv, const float* cos_tab, const float* sin_tab,
                     void* dqkv, float* dtheta, int B, int N, int heads, int hd, int n_extra, float q_scale, int dtype, lnx_stream_t s);
+/* same, when qkv holds the already scaled q cos s / k cos (written by lnx_qkv_rope_gemm; the un-scaled q / k were never stored) */
+int lnx_rope_qk_bwd_scaled(const void* dq, const void* dk, const void* dv, const void* qkv_scaled, const float* cos_tab, const float* sin_tab,
+                           void* dqkv, float* dtheta, int B, int N, int heads, int hd, int n_extra, float q_scale, int dtype, lnx_stream_t s);
 /* dfreqs[2,heads,half] += sum_n (tx[n], ty[n]) * dtheta[n,h,j] */
 int lnx_rope_freq_grad(const float* dtheta, float* dfreqs, int H, int W, int heads, int half, lnx_stream_t s);
 
@@ -181,6 +184,19 @@ int lnx_attn_fwd(const void* q, const void* k, const void* v, void* out, float* 
 /* delta_ws: 16-byte aligned float scratch of B*heads*N*(hd+1) + 4 elements (row deltas + fp32 dQ accumulator) */
 int lnx_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                  void* dq, void* dk, void* dv, float* delta_ws, int B, int heads, int N, int hd, int dtype, int force_simt, lnx_stream_t s);
+
+/* The qkv projection with the cos factors and the softmax scale applied in its epilogue (replaces self.qkv(x) + the q / k scaling of
+ * rope_2d_mhsa.py:432-501): qkv[M, 3 D] bf16 = x[M, K] w[3 D, K]^T + bias, q / k columns of the image tokens times
+ * cos(tx fx + ty fy) computed from freqs [2, D / 2] (the learnable frequencies, float32) in the epilogue, q columns times q_scale.
+ * M = B * tokens; the image tokens follow the n_extra leading tokens of each sequence and form a grid_w-wide grid.
+ * tcgen05 only (bf16): LNX_ERR_UNSUPPORTED otherwise. */
+int lnx_qkv_rope_gemm(const void* x, const void* w, const float* bias, const float* freqs, void* qkv, int64_t M, int D, int K,
+                      int tokens, int n_extra, int grid_w, float q_scale, lnx_stream_t s);
+/* attention reading q / k / v straight from that [B, N, 3, heads, hd] matrix (bf16, hd = 64, N <= 240); out [B,N,heads*hd], lse [B,heads,N] */
+int lnx_attn_qkv_fwd(const void* qkv, void* out, float* lse, int B, int heads, int N, int hd, int dtype, lnx_stream_t s);
+/* its backward: dq / dk / dv head-major [B,heads,N,hd] */
+int lnx_attn_qkv_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dq, void* dk, void* dv,
+                     int B, int heads, int N, int hd, int dtype, lnx_stream_t s);
 
 /* ---- tail ---------------------------------------------------------------- */
 /* out[b,d] = w[0]*a[b,d] + w[1]*c[b,d] + bias[0]   (Conv1d(2->1,k=1), mFormerV1.py:512-524) */

@@ -303,6 +303,28 @@ int lnx_attn_fwd_long_tc2(const void* q, const void* k, const void* v, void* out
 int lnx_attn_bwd_tc2(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, void* dq, void* dk,
                      void* dv, int B, int heads, int N, int hd, cudaStream_t st);
 
+int lnx_attn_bias_fwd_tc2(const void* qkv, const float* bias, void* out, float* lse, int B, int heads, int N, int hd, float scale, cudaStream_t st);
+int lnx_attn_qkv_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dq, void* dk, void* dv, int B, int heads,
+                         int N, int hd, cudaStream_t st);
+
+// Attention straight from the [B, N, 3, heads, hd] matrix of the (RoPE-fused) qkv projection: no head-major copies of q / k / v.
+// bf16, hd = 64, N <= 240 (the tcgen05 kernels); anything else is LNX_ERR_UNSUPPORTED and the caller keeps the split path.
+extern "C" int lnx_attn_qkv_fwd(const void* qkv, void* out, float* lse, int B, int heads, int N, int hd, int dtype, lnx_stream_t s) {
+  LNX_REQUIRE(qkv && out && lse, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && heads > 0 && N > 0, LNX_ERR_SHAPE);
+  if (dtype != LNX_BF16 || hd != 64) return LNX_ERR_UNSUPPORTED;
+  return lnx_attn_bias_fwd_tc2(qkv, nullptr, out, lse, B, heads, N, hd, 1.0f, (cudaStream_t)s);
+}
+
+// dq / dk / dv: head-major [B, heads, N, hd] bf16 (lnx_rope_qk_bwd_scaled turns them into dqkv)
+extern "C" int lnx_attn_qkv_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dq, void* dk, void* dv, int B,
+                                int heads, int N, int hd, int dtype, lnx_stream_t s) {
+  LNX_REQUIRE(qkv && out && dout && lse && dq && dk && dv, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && heads > 0 && N > 0, LNX_ERR_SHAPE);
+  if (dtype != LNX_BF16 || hd != 64 || N > 240) return LNX_ERR_UNSUPPORTED;
+  return lnx_attn_qkv_bwd_tc2(qkv, out, dout, lse, dq, dk, dv, B, heads, N, hd, (cudaStream_t)s);
+}
+
 extern "C" int lnx_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int heads, int N, int hd,
                             int dtype, int force_simt, lnx_stream_t s) {
   LNX_REQUIRE(q && k && v && out && lse, LNX_ERR_NULL);

@@ -542,7 +542,8 @@ __global__ void __launch_bounds__(448, 1) attn_fwd_long_tc2_kernel(const __grid_
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ tile 0 [384,448) | dQ tile 1 [448,512)
 struct BwdParams {
   int B, heads, N;
-  int n_t;  // 128-row tiles of the sequence (1 or 2)
+  int n_t;    // 128-row tiles of the sequence (1 or 2)
+  int qkv4d;  // 1: q / k / v are read straight from the [B, N, 3, heads, 64] qkv matrix (4-D tensor maps)
 };
 enum { B_LOAD = 0, B_SDP = 1, B_PDS = 2, B_ACC = 3, B_NBARS = 4 };
 
@@ -585,9 +586,15 @@ __global__ void __launch_bounds__(320, 1) attn_bwd_tc2_kernel(const __grid_const
     if (lane == 0) {
       mbar_expect_tx(&bars[B_LOAD], (uint32_t)(4 * p.n_t * 16384));
       for (int i = 0; i < p.n_t; ++i) {
-        tma_load_3d(sK + i * 16384, &tmK, &bars[B_LOAD], 0, i * QT, bh);
-        tma_load_3d(sV + i * 16384, &tmV, &bars[B_LOAD], 0, i * QT, bh);
-        tma_load_3d(sQ + i * 16384, &tmQ, &bars[B_LOAD], 0, i * QT, bh);
+        if (p.qkv4d) {
+          tma_load_4d(sK + i * 16384, &tmK, &bars[B_LOAD], 0, h, i * QT, b);
+          tma_load_4d(sV + i * 16384, &tmV, &bars[B_LOAD], 0, h, i * QT, b);
+          tma_load_4d(sQ + i * 16384, &tmQ, &bars[B_LOAD], 0, h, i * QT, b);
+        } else {
+          tma_load_3d(sK + i * 16384, &tmK, &bars[B_LOAD], 0, i * QT, bh);
+          tma_load_3d(sV + i * 16384, &tmV, &bars[B_LOAD], 0, i * QT, bh);
+          tma_load_3d(sQ + i * 16384, &tmQ, &bars[B_LOAD], 0, i * QT, bh);
+        }
         tma_load_3d(sdO + i * 16384, &tmdO, &bars[B_LOAD], h * HD, i * QT, b);  // dout is [B][N][heads*64]
       }
     }
@@ -774,7 +781,7 @@ int lnx_attn_fwd_tc2(const void* q, const void* k, const void* v, void* out, flo
 
 // softmax(scale q k^T + bias[h]) v with q/k/v read straight from qkv [B, N, 3, heads, hd] (hd <= 64, N <= 240): the
 // RelativeAttention of mFormerV0.  Head dims below 64 ride on the TMA out-of-bounds zero fill (tiles stay [rows][64]).
-int lnx_attn_bias_fwd_tc2(const void* qkv, const float* bias, void* out, int B, int heads, int N, int hd, float scale, cudaStream_t st) {
+int lnx_attn_bias_fwd_tc2(const void* qkv, const float* bias, void* out, float* lse, int B, int heads, int N, int hd, float scale, cudaStream_t st) {
   if (hd > HD || hd % 16 != 0 || N > 240 || N < 1) return LNX_ERR_UNSUPPORTED;
   if (!lnx_aligned16(qkv) || !lnx_aligned16(out)) return LNX_ERR_UNSUPPORTED;
   if (bias && (N % 4 != 0 || !lnx_aligned16(bias))) return LNX_ERR_UNSUPPORTED;  // the bias rows are staged with 16-byte loads
@@ -805,8 +812,8 @@ int lnx_attn_bias_fwd_tc2(const void* qkv, const float* bias, void* out, int B, 
     if (e != cudaSuccess) return lnx_set_cuda_error(e);
     set = (int)smem;
   }
-  if (bias) attn_fwd_tc2_kernel<true><<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tm[0], tm[1], tm[2], (bf16*)out, nullptr, p);
-  else attn_fwd_tc2_kernel<false><<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tm[0], tm[1], tm[2], (bf16*)out, nullptr, p);
+  if (bias) attn_fwd_tc2_kernel<true><<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tm[0], tm[1], tm[2], (bf16*)out, lse, p);
+  else attn_fwd_tc2_kernel<false><<<min(p.n_bh, kNumSMs), 448, smem, st>>>(tm[0], tm[1], tm[2], (bf16*)out, lse, p);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
@@ -832,15 +839,27 @@ int lnx_attn_fwd_long_tc2(const void* q, const void* k, const void* v, void* out
   return LNX_OK;
 }
 
-// dq / dk / dv are written as bf16 (no accumulation, no workspace)
-int lnx_attn_bwd_tc2(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, void* dq, void* dk,
-                     void* dv, int B, int heads, int N, int hd, cudaStream_t st) {
+// dq / dk / dv are written as bf16 (no accumulation, no workspace), head-major [B * heads, N, 64].  qkv != nullptr: q / k / v are read
+// straight from the [B, N, 3, heads, 64] matrix the (RoPE-fused) qkv projection wrote, instead of head-major copies.
+static int attn_bwd_tc2_launch(const void* q, const void* k, const void* v, const void* qkv, const void* out, const void* dout, const float* lse,
+                               void* dq, void* dk, void* dv, int B, int heads, int N, int hd, cudaStream_t st) {
   if (hd != HD || N > 256 || N < 1) return LNX_ERR_UNSUPPORTED;
   BwdParams p;
   p.B = B; p.heads = heads; p.N = N;
   p.n_t = (N + QT - 1) / QT;
+  p.qkv4d = qkv ? 1 : 0;
   CUtensorMap tq, tk, tv, tdo;
-  if (!head_tmap(&tq, q, B * heads, N, QT) || !head_tmap(&tk, k, B * heads, N, QT) || !head_tmap(&tv, v, B * heads, N, QT)) return LNX_ERR_UNSUPPORTED;
+  if (qkv) {
+    CUtensorMap* tm[3] = {&tq, &tk, &tv};
+    for (int which = 0; which < 3; ++which) {
+      const long long dims[4] = {HD, heads, N, B};
+      const long long strides[3] = {HD, 3LL * heads * HD, (long long)N * 3 * heads * HD};
+      const int box[4] = {HD, 1, QT, 1};
+      if (!make_tmap(tm[which], reinterpret_cast<const bf16*>(qkv) + (long long)which * heads * HD, 4, dims, strides, box)) return LNX_ERR_UNSUPPORTED;
+    }
+  } else if (!head_tmap(&tq, q, B * heads, N, QT) || !head_tmap(&tk, k, B * heads, N, QT) || !head_tmap(&tv, v, B * heads, N, QT)) {
+    return LNX_ERR_UNSUPPORTED;
+  }
   {  // dout [B][N][heads*64]: box {64, 128, 1} at column h*64
     const long long dims[3] = {(long long)heads * HD, N, B};
     const long long strides[2] = {(long long)heads * HD, (long long)N * heads * HD};
@@ -857,4 +876,14 @@ int lnx_attn_bwd_tc2(const void* q, const void* k, const void* v, const void* ou
   attn_bwd_tc2_kernel<<<B * heads, 320, smem, st>>>(tq, tk, tv, tdo, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dq, (bf16*)dk, (bf16*)dv, p);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
+}
+
+int lnx_attn_bwd_tc2(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse, void* dq, void* dk,
+                     void* dv, int B, int heads, int N, int hd, cudaStream_t st) {
+  return attn_bwd_tc2_launch(q, k, v, nullptr, out, dout, lse, dq, dk, dv, B, heads, N, hd, st);
+}
+
+int lnx_attn_qkv_bwd_tc2(const void* qkv, const void* out, const void* dout, const float* lse, void* dq, void* dk, void* dv, int B, int heads,
+                         int N, int hd, cudaStream_t st) {
+  return attn_bwd_tc2_launch(nullptr, nullptr, nullptr, qkv, out, dout, lse, dq, dk, dv, B, heads, N, hd, st);
 }

@@ -18,6 +18,13 @@ struct GemmArgs {
   const float* row_scale;  // per row-group multiplier (DropPath): row_scale[m / rows_per_group]
   int rows_per_group;
   int accumulate;
+  // Token-position factors (the reference's cos "RoPE", rope_2d_mhsa.py:432-501, folded into the qkv projection; tcgen05 path only):
+  // columns n < 2 tok_dim of row m are multiplied by cos(tx fx[p] + ty fy[p]), p = (n % tok_dim) / 2, fx = tok_scale[p],
+  // fy = tok_scale[tok_dim / 2 + p], (tx, ty) = (pos % tok_w, pos / tok_w), pos = m % tok_period - tok_extra (factor 1 for the
+  // tok_extra leading tokens of every sequence); columns n < tok_dim also by tok_qscale.
+  const float* tok_scale = nullptr;  // the learnable frequencies [2, tok_dim / 2]
+  int tok_period = 1, tok_extra = 0, tok_dim = 0, tok_w = 1;
+  float tok_qscale = 1.f;
 };
 
 // v = acc -> epilogue value for element (m, n) at flat index idx (pitch N)

@@ -433,6 +433,23 @@ int lnx_gemm_tc(const GemmArgs& g, int c_dtype, cudaStream_t st) {
   return LNX_ERR_DTYPE;
 }
 
+// qkv[M, 3 D] = (x[M, K] w[3 D, K]^T + bias) with the cos factors of the reference's 2-D "RoPE" and the softmax scale applied to the
+// q / k columns in the epilogue (bf16, tcgen05 path only): replaces nn.Linear + the separate q / k scaling pass of
+// rope_2d_mhsa.py:432-501.  freqs [2, D / 2] float32 = the learnable (fx, fy) per (head, pair); image tokens form a grid_w-wide grid
+// after the n_extra leading tokens of each sequence of `tokens` rows.
+extern "C" int lnx_qkv_rope_gemm(const void* x, const void* w, const float* bias, const float* freqs, void* qkv, int64_t M, int D, int K,
+                                 int tokens, int n_extra, int grid_w, float q_scale, lnx_stream_t s) {
+  LNX_REQUIRE(x && w && freqs && qkv, LNX_ERR_NULL);
+  LNX_REQUIRE(M > 0 && M < (1ll << 31) && D > 0 && K > 0 && tokens > 0 && n_extra >= 0 && n_extra <= tokens && grid_w > 0, LNX_ERR_SHAPE);
+  GemmArgs g;
+  g.A = x; g.B = w; g.C = qkv; g.lda = K; g.ldb = K; g.M = (int)M; g.N = 3 * D; g.K = K;
+  g.a_trans = 0; g.b_trans = 0;
+  g.bias = bias; g.act = LNX_ACT_NONE; g.aux_out = nullptr; g.act_grad_in = nullptr; g.residual = nullptr; g.col_scale = nullptr;
+  g.row_scale = nullptr; g.rows_per_group = 0; g.accumulate = 0;
+  g.tok_scale = freqs; g.tok_period = tokens; g.tok_extra = n_extra; g.tok_dim = D; g.tok_w = grid_w; g.tok_qscale = q_scale;
+  return lnx_gemm_tc2(g, nullptr, (cudaStream_t)s);
+}
+
 // ------------------------------------------------------------------ public dispatcher
 extern "C" int lnx_gemm(int ab_dtype, const void* A, int64_t lda, int a_trans, const void* B, int64_t ldb, int b_trans, void* C,
                         int c_dtype, int M, int N, int K, const float* bias, int act, void* aux_out, const void* act_grad_in,

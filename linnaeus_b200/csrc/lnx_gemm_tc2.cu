@@ -360,6 +360,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
       const bool row_ok = m < p.M;
       float rs = 1.f;
       if (SCALE) rs = (g.row_scale && row_ok) ? g.row_scale[m / g.rows_per_group] : 1.f;
+      int tok_pos = -1;  // image-token index of this row within its sequence (token-position factors)
+      if (SCALE && g.tok_scale && row_ok) tok_pos = m % g.tok_period - g.tok_extra;
+      const float tok_tx = (float)(tok_pos >= 0 ? tok_pos % g.tok_w : 0), tok_ty = (float)(tok_pos >= 0 ? tok_pos / g.tok_w : 0);
       mbar_wait(&tfull_bar[as], aph);
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + as * TMEM_STAGE_COLS + ((uint32_t)(q * 32) << 16);
@@ -378,6 +381,24 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
         if (IN_KIND) {
           mbar_wait(my_in, in_cnt & 1u);
           ++in_cnt;
+        }
+        // token-position factors of this 64-column block (32 pairs): cos(tx fx + ty fy) straight from the learnable frequencies --
+        // the two frequency rows are warp-uniform (broadcast loads, 1.5 KB per layer) and the cosine is one MUFU op, so nothing
+        // per-element is read from memory (a [pair][position] table cost +34 us per projection, more than the pass it replaced)
+        float tokf[32];
+        const bool tok_on = SCALE && g.tok_scale && nb0 < 2 * g.tok_dim;
+        if (tok_on) {
+          const float qs = nb0 < g.tok_dim ? g.tok_qscale : 1.f;
+          const float* fx = g.tok_scale + ((nb0 < g.tok_dim ? nb0 : nb0 - g.tok_dim) >> 1);
+          const float* fy = fx + (g.tok_dim >> 1);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(fx + i)), c = __ldg(reinterpret_cast<const float4*>(fy + i));
+            tokf[i] = tok_pos >= 0 ? __cosf(fmaf(tok_tx, a.x, tok_ty * c.x)) * qs : qs;
+            tokf[i + 1] = tok_pos >= 0 ? __cosf(fmaf(tok_tx, a.y, tok_ty * c.y)) * qs : qs;
+            tokf[i + 2] = tok_pos >= 0 ? __cosf(fmaf(tok_tx, a.z, tok_ty * c.z)) * qs : qs;
+            tokf[i + 3] = tok_pos >= 0 ? __cosf(fmaf(tok_tx, a.w, tok_ty * c.w)) * qs : qs;
+          }
         }
         float csum[2] = {0.f, 0.f};
 #pragma unroll
@@ -438,7 +459,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1)
                 for (int i = 0; i < 8; ++i) vv[i] = swish_fast(vv[i]);
               }
               if (SCALE) {
-                if (g.col_scale && n < p.N) {
+                if (g.tok_scale) {
+                  if (tok_on) {  // q / k columns: cos factor of the token position (pairs share one), q also the softmax scale
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vv[i] *= tokf[jg * 4 + (i >> 1)];
+                  }
+                } else if (g.col_scale && n < p.N) {
                   const float4 s0 = __ldg(reinterpret_cast<const float4*>(g.col_scale + n));
                   const float4 s1 = __ldg(reinterpret_cast<const float4*>(g.col_scale + n) + 1);
                   vv[0] *= s0.x * rs; vv[1] *= s0.y * rs; vv[2] *= s0.z * rs; vv[3] *= s0.w * rs;
@@ -663,7 +689,9 @@ int lnx_gemm_tc2(const GemmArgs& g, float* colsum_out, cudaStream_t st) {
   L.colsum_out = colsum_out;
   L.grid = min(p.tiles_m * p.tiles_n, kNumSMs);
   L.st = st;
-  const bool aux = g.aux_out != nullptr, scale = g.col_scale || g.row_scale, colsum = colsum_out != nullptr;
+  const bool aux = g.aux_out != nullptr, scale = g.col_scale || g.row_scale || g.tok_scale, colsum = colsum_out != nullptr;
+  if (g.tok_scale && (in_kind || aux || colsum || g.col_scale || g.row_scale || g.act != LNX_ACT_NONE || g.tok_dim % 64 != 0 || g.tok_w <= 0 || !lnx_aligned16(g.tok_scale)))
+    return LNX_ERR_UNSUPPORTED;
   switch (g.act) {
     case LNX_ACT_NONE: return launch_none(L, in_kind, aux, scale, colsum);
     case LNX_ACT_GELU: return launch_act<LNX_ACT_GELU>(L, in_kind, aux, scale, colsum);

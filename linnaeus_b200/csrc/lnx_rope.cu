@@ -104,7 +104,10 @@ __global__ void rope_qk_fwd_kernel(const T* __restrict__ qkv, const float* __res
 }
 
 // grid: (N, batch chunks); thread = (which in {q,k,v}, head, pair-chunk of 4 pairs)
-template <typename T>
+// ROT: qkv holds the ALREADY scaled q' = q cos s / k' = k cos (the qkv projection applied the factors in its epilogue), so
+// g q s (-sin) = -g q' tan(theta).  bf16 keeps its 8 relative bits down to 1e-38, so q' = q cos s is as informative as q even where cos
+// is tiny (the term there is the LARGEST, |sin| ~ 1: it must not be dropped); only an exactly vanishing cos loses it.
+template <typename T, bool ROT>
 __global__ void rope_qk_bwd_kernel(const T* __restrict__ dq, const T* __restrict__ dk, const T* __restrict__ dv,
                                    const T* __restrict__ qkv, const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
                                    T* __restrict__ dqkv, float* __restrict__ dtheta, int B, int N, int heads, int hd, int n_extra,
@@ -125,6 +128,9 @@ __global__ void rope_qk_bwd_kernel(const T* __restrict__ dq, const T* __restrict
       for (int e = 0; e < 4; ++e) c[e] = cos_tab[o + e], sn[e] = sin_tab[o + e];
     }
     const float sc = (which == 0) ? q_scale : 1.0f;
+    float mt[4];  // multiplier of g * x in dtheta
+#pragma unroll
+    for (int e = 0; e < 4; ++e) mt[e] = ROT ? (fabsf(c[e]) > 1e-30f ? -sn[e] / c[e] : 0.f) : -sn[e] * sc;
     float dth[4] = {0.f, 0.f, 0.f, 0.f};
     const T* gsrc = (which == 0 ? dq : which == 1 ? dk : dv);
 #pragma unroll 4
@@ -136,7 +142,7 @@ __global__ void rope_qk_bwd_kernel(const T* __restrict__ dq, const T* __restrict
       if (which < 2 && img) {
         ld8<T>(qkv + o, x);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dth[e >> 1] += g[e] * x[e] * sc * (-sn[e >> 1]);
+        for (int e = 0; e < 8; ++e) dth[e >> 1] += g[e] * x[e] * mt[e >> 1];
       }
       if (which < 2) {
 #pragma unroll
@@ -206,7 +212,7 @@ extern "C" int lnx_rope_qk_fwd(const void* qkv, const float* cos_tab, void* q, v
   return LNX_OK;
 }
 
-extern "C" int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, const void* qkv, const float* cos_tab, const float* sin_tab,
+static int rope_qk_bwd_launch(bool rot, const void* dq, const void* dk, const void* dv, const void* qkv, const float* cos_tab, const float* sin_tab,
                                void* dqkv, float* dtheta, int B, int N, int heads, int hd, int n_extra, float q_scale, int dtype,
                                lnx_stream_t s) {
   LNX_REQUIRE(dq && dk && dv && qkv && cos_tab && sin_tab && dqkv && dtheta, LNX_ERR_NULL);
@@ -232,13 +238,26 @@ extern "C" int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, c
   dim3 grid(N, by);
   cudaStream_t st = (cudaStream_t)s;
   if (dtype == LNX_F32)
-    rope_qk_bwd_kernel<float><<<grid, threads, 0, st>>>((const float*)dq, (const float*)dk, (const float*)dv, (const float*)qkv, cos_tab, sin_tab, (float*)dqkv, dtheta, B, N, heads, hd, n_extra, q_scale, bpb);
+    (rot ? rope_qk_bwd_kernel<float, true> : rope_qk_bwd_kernel<float, false>)<<<grid, threads, 0, st>>>((const float*)dq, (const float*)dk, (const float*)dv, (const float*)qkv, cos_tab, sin_tab, (float*)dqkv, dtheta, B, N, heads, hd, n_extra, q_scale, bpb);
   else if (dtype == LNX_BF16)
-    rope_qk_bwd_kernel<bf16><<<grid, threads, 0, st>>>((const bf16*)dq, (const bf16*)dk, (const bf16*)dv, (const bf16*)qkv, cos_tab, sin_tab, (bf16*)dqkv, dtheta, B, N, heads, hd, n_extra, q_scale, bpb);
+    (rot ? rope_qk_bwd_kernel<bf16, true> : rope_qk_bwd_kernel<bf16, false>)<<<grid, threads, 0, st>>>((const bf16*)dq, (const bf16*)dk, (const bf16*)dv, (const bf16*)qkv, cos_tab, sin_tab, (bf16*)dqkv, dtheta, B, N, heads, hd, n_extra, q_scale, bpb);
   else
     return LNX_ERR_DTYPE;
   LNX_CHECK_LAUNCH();
   return LNX_OK;
+}
+
+extern "C" int lnx_rope_qk_bwd(const void* dq, const void* dk, const void* dv, const void* qkv, const float* cos_tab, const float* sin_tab,
+                               void* dqkv, float* dtheta, int B, int N, int heads, int hd, int n_extra, float q_scale, int dtype,
+                               lnx_stream_t s) {
+  return rope_qk_bwd_launch(false, dq, dk, dv, qkv, cos_tab, sin_tab, dqkv, dtheta, B, N, heads, hd, n_extra, q_scale, dtype, s);
+}
+
+// Same, for the fused projection (lnx_qkv_rope_gemm): qkv_scaled holds q cos s / k cos / v, the un-scaled q / k were never stored.
+extern "C" int lnx_rope_qk_bwd_scaled(const void* dq, const void* dk, const void* dv, const void* qkv_scaled, const float* cos_tab,
+                                      const float* sin_tab, void* dqkv, float* dtheta, int B, int N, int heads, int hd, int n_extra,
+                                      float q_scale, int dtype, lnx_stream_t s) {
+  return rope_qk_bwd_launch(true, dq, dk, dv, qkv_scaled, cos_tab, sin_tab, dqkv, dtheta, B, N, heads, hd, n_extra, q_scale, dtype, s);
 }
 
 extern "C" int lnx_rope_freq_grad(const float* dtheta, float* dfreqs, int H, int W, int heads, int half, lnx_stream_t s) {

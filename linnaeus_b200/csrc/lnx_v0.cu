@@ -684,7 +684,7 @@ extern "C" int lnx_se_scale(const void* x, const float* gate, void* y, int B, in
   return LNX_OK;
 }
 
-int lnx_attn_bias_fwd_tc2(const void* qkv, const float* bias, void* out, int B, int heads, int N, int hd, float scale, cudaStream_t st);
+int lnx_attn_bias_fwd_tc2(const void* qkv, const float* bias, void* out, float* lse, int B, int heads, int N, int hd, float scale, cudaStream_t st);
 
 extern "C" int lnx_attn_bias_fwd(const void* qkv, const float* bias, void* out, int B, int heads, int N, int hd, float scale, int dtype,
                                  lnx_stream_t s) {
@@ -692,7 +692,7 @@ extern "C" int lnx_attn_bias_fwd(const void* qkv, const float* bias, void* out, 
   LNX_REQUIRE(B > 0 && heads > 0 && N > 0, LNX_ERR_SHAPE);
   LNX_REQUIRE(dtype == LNX_F32 || dtype == LNX_BF16, LNX_ERR_DTYPE);
   if (dtype == LNX_BF16) {  // tcgen05 path: head_dim <= 64, N <= 240 (persistent pipelined kernel of lnx_attn_tc2.cu)
-    const int r = lnx_attn_bias_fwd_tc2(qkv, bias, out, B, heads, N, hd, scale, (cudaStream_t)s);
+    const int r = lnx_attn_bias_fwd_tc2(qkv, bias, out, nullptr, B, heads, N, hd, scale, (cudaStream_t)s);
     if (r != LNX_ERR_UNSUPPORTED) return r;
     if (getenv("LNX_ATTN_NO_FALLBACK") && hd <= 64 && N <= 240) return LNX_ERR_UNSUPPORTED;
   }

@@ -109,6 +109,34 @@ def wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, x_ld: int | None = None, out: t
 
 
 # --------------------------------------------------------------------------- Linear
+def _linear_param_grads(weight, bias, dpre, dpre_w, x2, lda, N, K, want_dw, want_db):
+    """dW = dpre^T x and db = colsum(dpre) of a Linear layer, accumulated straight into the parameters' gradient sinks when they
+    exist (then (None, None) is returned); the bias gradient rides on the weight-gradient GEMM when the dtypes allow."""
+    dw = db = None
+    sb = _sink(bias) if want_db else None
+    db_buf = None
+    if want_db:
+        db_buf = sb if sb is not None else torch.zeros(N, dtype=torch.float32, device=dpre.device)
+    db_done = False
+    if want_dw:
+        sw = _sink(weight)
+        fuse_db = want_db and dpre_w is dpre  # the bias gradient rides on the weight-gradient GEMM
+        if sw is not None:
+            wgrad(dpre_w, x2, x_ld=lda, out=sw.view(N, K), db_out=db_buf if fuse_db else None)
+            _grad_done(weight)
+        else:
+            dw = wgrad(dpre_w, x2, x_ld=lda, db_out=db_buf if fuse_db else None)
+        db_done = fuse_db
+    if want_db:
+        if not db_done:
+            colsum(dpre, out=db_buf)
+        if sb is not None:
+            _grad_done(bias)
+        else:
+            db = db_buf
+    return dw, db
+
+
 class _Linear(torch.autograd.Function):
     """y = act(x W^T + b) (+ residual).  nn.Linear (+GELU/ReLU) of the reference."""
 
@@ -167,28 +195,8 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dpre_w, wc, M, K, N, b_trans=True, ldb=K).view(xshape)
         weight, bias = ctx.params
-        want_db = has_bias and ctx.needs_input_grad[2]
-        sb = _sink(bias) if want_db else None
-        db_buf = None
-        if want_db:
-            db_buf = sb if sb is not None else torch.zeros(N, dtype=torch.float32, device=dpre.device)
-        db_done = False
-        if ctx.needs_input_grad[1]:
-            sw = _sink(weight)
-            fuse_db = want_db and dpre_w is dpre  # the bias gradient rides on the weight-gradient GEMM
-            if sw is not None:
-                wgrad(dpre_w, x2, x_ld=lda, out=sw.view(N, K), db_out=db_buf if fuse_db else None)
-                _grad_done(weight)
-            else:
-                dw = wgrad(dpre_w, x2, x_ld=lda, db_out=db_buf if fuse_db else None)
-            db_done = fuse_db
-        if want_db:
-            if not db_done:
-                colsum(dpre, out=db_buf)
-            if sb is not None:
-                _grad_done(bias)
-            else:
-                db = db_buf
+        dw, db = _linear_param_grads(weight, bias if has_bias else None, dpre, dpre_w, x2, lda, N, K, ctx.needs_input_grad[1],
+                                     has_bias and ctx.needs_input_grad[2])
         return dx, dw, db, None, None, d_res, None, None, None, None, None
 
 
@@ -621,6 +629,83 @@ class _RopeAttention(torch.autograd.Function):
 
 def rope_attention(qkv, freqs, H, W, heads, n_extra):
     return _RopeAttention.apply(qkv, freqs, H, W, heads, n_extra)
+
+
+FUSED_QKV_ROPE = True  # tests flip this to compare against the split path (Linear -> rope_qk_fwd -> attention)
+
+
+def fused_qkv_rope_ok(x: torch.Tensor, dim: int, heads: int, n_tokens: int) -> bool:
+    """The fused projection + attention path covers bf16, head_dim 64, <= 240 tokens (the tcgen05 attention kernels)."""
+    return (FUSED_QKV_ROPE and not FORCE_SIMT and x.dtype == torch.bfloat16 and dim == heads * 64 and n_tokens <= 240
+            and x.shape[-1] % 8 == 0)
+
+
+class _QkvRopeAttention(torch.autograd.Function):
+    """x [B,N,K] -> softmax((q cos s)(k cos)^T) v [B,N,D] with q/k/v = x W^T + b   (rope_2d_mhsa.py:432-501, self.qkv included).
+
+    The cos factors and the softmax scale are applied in the epilogue of the projection GEMM (lnx_qkv_rope_gemm) and the attention
+    kernels read q / k / v straight from its [B,N,3,heads,64] output through 4-D tensor maps: no separate scaling pass, no head-major
+    copies.  Backward: attention -> dq/dk/dv (head-major) -> lnx_rope_qk_bwd_scaled (factors, d theta from the scaled q / k,
+    token-major dqkv) -> the Linear gradients."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, weight_c, freqs, H, W, heads, n_extra, grad_on=True):
+        B, N, K = x.shape
+        D = weight.shape[0] // 3
+        hd = D // heads
+        half = hd // 2
+        x2 = _c(x).view(-1, K)
+        dev = x.device
+        wc = weight_c if weight_c is not None else compute_copy(weight, x2.dtype)
+        need_grad = grad_on and any(ctx.needs_input_grad)
+        fr = _c(freqs.detach().float())
+        scale = float(hd) ** -0.5
+        qkv = torch.empty((B, N, 3 * D), dtype=x2.dtype, device=dev)
+        call("lnx_qkv_rope_gemm", x2.data_ptr(), wc.data_ptr(), ptr(bias), fr.data_ptr(), qkv.data_ptr(), B * N, D, K, N, n_extra, W, scale)
+        out = torch.empty((B, N, D), dtype=x2.dtype, device=dev)
+        lse = torch.empty((B, heads, N), dtype=torch.float32, device=dev)
+        call("lnx_attn_qkv_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, heads, N, hd, dt(qkv))
+        if need_grad:
+            ctx.save_for_backward(x2, wc, qkv, out, lse, fr)
+            ctx.params = (weight, bias, freqs)
+            ctx.dims = (B, N, K, D, heads, hd, half, H, W, n_extra, scale, freqs.shape, x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, wc, qkv, out, lse, fr = ctx.saved_tensors
+        B, N, K, D, heads, hd, half, H, W, n_extra, scale, fshape, xshape = ctx.dims
+        weight, bias, freqs = ctx.params
+        dev = qkv.device
+        dout = _c(dout)
+        cos = torch.empty((H * W, heads, half), dtype=torch.float32, device=dev)  # [position][pair] tables of the backward kernel
+        sin = torch.empty_like(cos)
+        call("lnx_rope_table", fr.data_ptr(), cos.data_ptr(), sin.data_ptr(), H, W, heads, half)
+        dqkv_h = torch.empty((3, B, heads, N, hd), dtype=qkv.dtype, device=dev)
+        call("lnx_attn_qkv_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv_h[0].data_ptr(), dqkv_h[1].data_ptr(),
+             dqkv_h[2].data_ptr(), B, heads, N, hd, dt(qkv))
+        dqkv = torch.empty_like(qkv)
+        dtheta = torch.zeros((H * W, heads, half), dtype=torch.float32, device=dev)
+        call("lnx_rope_qk_bwd_scaled", dqkv_h[0].data_ptr(), dqkv_h[1].data_ptr(), dqkv_h[2].data_ptr(), qkv.data_ptr(), cos.data_ptr(),
+             sin.data_ptr(), dqkv.data_ptr(), dtheta.data_ptr(), B, N, heads, hd, n_extra, scale, dt(qkv))
+        dfreqs = None
+        if ctx.needs_input_grad[4]:
+            s_f = _sink(freqs)
+            dfreqs = s_f if s_f is not None else torch.zeros(fshape, dtype=torch.float32, device=dev)
+            call("lnx_rope_freq_grad", dtheta.data_ptr(), dfreqs.data_ptr(), H, W, heads, half)  # dfreqs +=
+            if s_f is not None:
+                _grad_done(freqs)
+                dfreqs = None
+        M = B * N
+        dqkv2 = dqkv.view(M, 3 * D)
+        dx = gemm(dqkv2, wc, M, K, 3 * D, b_trans=True, ldb=K).view(xshape) if ctx.needs_input_grad[0] else None
+        dw, db = _linear_param_grads(weight, bias, dqkv2, dqkv2, x2, K, 3 * D, K, ctx.needs_input_grad[1],
+                                     bias is not None and ctx.needs_input_grad[2])
+        return dx, dw, db, None, dfreqs, None, None, None, None, None
+
+
+def qkv_rope_attention(x, weight, bias, weight_c, freqs, H, W, heads, n_extra):
+    return _QkvRopeAttention.apply(x, weight, bias, weight_c, freqs, H, W, heads, n_extra, torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------- aggregate

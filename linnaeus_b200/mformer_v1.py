@@ -249,9 +249,13 @@ class RoPE2DMHSABlock(nn.Module):
     def run(self, x: torch.Tensor, H: int, W: int) -> torch.Tensor:
         a = self.attn
         t, x = F.layernorm_fork(x, self.norm1.weight, self.norm1.bias, 1e-5)  # x: skip connection (gradient fused into LN bwd)
-        qkv = F.linear(t, a.qkv.weight, a.qkv.bias, weight_c=_wc(a.qkv.weight))
-        o = F.rope_attention(qkv, a.freqs, H, W, a.num_heads, self.extra_token_num)
         B, N = x.shape[0], x.shape[1]
+        if F.fused_qkv_rope_ok(t, a.qkv.weight.shape[1], a.num_heads, N):
+            # projection with the cos factors in its epilogue, attention straight from its output (no q / k scaling pass, no copies)
+            o = F.qkv_rope_attention(t, a.qkv.weight, a.qkv.bias, _wc(a.qkv.weight), a.freqs, H, W, a.num_heads, self.extra_token_num)
+        else:
+            qkv = F.linear(t, a.qkv.weight, a.qkv.bias, weight_c=_wc(a.qkv.weight))
+            o = F.rope_attention(qkv, a.freqs, H, W, a.num_heads, self.extra_token_num)
         m1 = drop_path_mask(B, self.drop_prob, self.training, x.device)
         x = F.linear(o, a.proj.weight, a.proj.bias, weight_c=_wc(a.proj.weight), residual=x, row_scale=m1, rows_per_group=N)
         t, x = F.layernorm_fork(x, self.norm2.weight, self.norm2.bias, 1e-5)
