@@ -34,8 +34,15 @@ FWD_GFLOP = {"sm": 8.659, "md": 12.505, "xl": 448.16}  # per image (SURVEY.md se
 FWD_GFLOP_V0 = {"sm": 8.94}
 FMA_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # fp32 FMA pipe: 148 SMs x 128 lanes x 2 flop at 1965 MHz (no measured figure)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/ (bf16, B = 256 shapes)
-NCU_TRAFFIC_BYTES = {
-    "mlp_fused_fwd_kernel C=96 M=802816": 308.5e6 + 125.6e6,  # profiles/r02_kernels_summary.md
+NCU_TRAFFIC_BYTES = {  # profiles/r02_kernels_summary.md (read + write)
+    "dwconv7_fwd_x2_kernel 256x56x56x96 (forward; the data gradient is the same kernel + fused skip)": 283.2e6 + 133.8e6,
+    "dwconv7_wgrad_x2_kernel 256x56x56x96": 426.2e6 + 4.8e6,
+    "mlp_fused_fwd_kernel C=96 M=802816": 308.5e6 + 126.1e6,
+    "mlp_fused_bwd_kernel C=96 M=802816": 308.5e6 + 1335.0e6,
+    "wgrad_tc_kernel dW1 384x96 K=802816": 771.0e6 + 4.2e6,
+    "wgrad_tc_kernel dW2 96x384 K=802816": 771.0e6 + 4.4e6,
+    "ln_bwd_bf16_kernel 802816x96": 314.7e6 + 126.2e6,
+    "attn_bwd_tc2_kernel 256x6x200x64": 197.9e6 + 83.8e6,
 }
 
 
@@ -510,7 +517,7 @@ def roofline_table(cx: Ctx, B: int, step_ms: float, hbm: float, tf_sus: float):
     gamma = torch.rand(C0, device=dev) + 0.5
     out = torch.empty_like(x2)
     add(f"mlp_fused_fwd_kernel C=96 M={M0}", lambda: F.mlp_fused_fwd(x2, w1, b1, w2, b2, gamma=gamma, residual=g2, out=out), 3, "hbm",
-        alg_bytes=3 * M0 * C0 * 2, note="x, residual read, y written; MUFU.TANH (half rate) is the co-limiter: 4 C tanh per row")
+        alg_bytes=3 * M0 * C0 * 2, note="x, residual read, y written; its own tile pipeline is the limiter (weights resident: ~56 KB of loads in flight per SM), see profiles/r02_microbench.md")
     h, dpre, _ = F.mlp_fused_bwd(x2, g2, w1, b1, w2)
     add(f"mlp_fused_bwd_kernel C=96 M={M0}", lambda: F.mlp_fused_bwd(x2, g2, w1, b1, w2), 3, "hbm", alg_bytes=11 * M0 * C0 * 2,
         note="x, dY read; h, dPre (4C wide) and dX written: write-bandwidth bound")

@@ -56,6 +56,12 @@ bench("gemm dPre     (x saved gelu')      802816x384x96", lambda: F.gemm(dy, w2,
 bench("gemm dX                            802816x96x384", lambda: F.gemm(dpre, w1, M, C, Hd, b_trans=True, ldb=C, out=y), (M * Hd + M * C) * e, 2 * M * C * Hd)
 bench("wgrad dW1+db1                      384x96 K=802816", lambda: F.wgrad(dpre, xln, out=dw1, db_out=db1), (M * Hd + M * C) * e, 2 * M * C * Hd)
 bench("wgrad dW2+db2                      96x384 K=802816", lambda: F.wgrad(dy, h, out=dw2, db_out=db2), (M * Hd + M * C) * e, 2 * M * C * Hd)
+# the single-kernel pointwise pair (what the train step launches at C = 96) -- same tensors
+w2e = (w2.float() * gam[:, None]).to(bf)
+bench("mlp fused fwd (pw1+GELU+pw2+gamma+res) 802816x96", lambda: F.mlp_fused_fwd(xln, w1, b1, w2, gam, gamma=gam, residual=res, out=y), 3 * M * C * e, 4 * M * C * Hd)
+bench("mlp fused bwd (recompute; h, dPre, dX) 802816x96", lambda: call("lnx_mlp_fused_bwd", xln.data_ptr(), dy.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2e.data_ptr(), h.data_ptr(), dpre.data_ptr(), y.data_ptr(), M, C, Hd), (3 * M * C + 2 * M * Hd) * e, 6 * M * C * Hd)
+bench("mlp fused bwd, dX only                 802816x96", lambda: call("lnx_mlp_fused_bwd", xln.data_ptr(), dy.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2e.data_ptr(), None, None, y.data_ptr(), M, C, Hd), 3 * M * C * e, 6 * M * C * Hd)
+bench("mlp fused wgrad (dW1, db1, dW2 on chip) 802816x96", lambda: call("lnx_mlp_fused_wgrad", xln.data_ptr(), dy.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2e.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), M, C, Hd), 2 * M * C * e, 8 * M * C * Hd)
 del h, dg, dpre
 
 # ---- transformer stage 2 GEMMs (tensor bound)
@@ -73,6 +79,8 @@ y2 = torch.empty(M2, D, device=dev, dtype=bf)
 dwf = torch.zeros(4 * D, D, device=dev)
 dbf = torch.zeros(4 * D, device=dev)
 bench("gemm qkv                           51200x1152x384", lambda: F.gemm(x, wq, M2, 3 * D, D, out=oq, bias=bq), None, 2 * M2 * 3 * D * D)
+frq = 0.3 * torch.randn(2, 6, 32, device=dev)
+bench("gemm qkv + cos-RoPE epilogue       51200x1152x384", lambda: call("lnx_qkv_rope_gemm", x.data_ptr(), wq.data_ptr(), bq.data_ptr(), frq.data_ptr(), oq.data_ptr(), M2, D, D, 200, 4, 14, 0.125), None, 2 * M2 * 3 * D * D)
 bench("gemm fc1 (GELU, saves gelu')       51200x1536x384", lambda: F.gemm(x, wf1, M2, 4 * D, D, out=hh, bias=bf1, act=3, aux_out=dgg), None, 2 * M2 * 4 * D * D)
 bench("gemm fc2 (+residual)               51200x384x1536", lambda: F.gemm(hh, wf2, M2, D, 4 * D, out=y2, bias=bf2, residual=x), None, 2 * M2 * 4 * D * D)
 bench("gemm dPre fc1                      51200x1536x384", lambda: F.gemm(y2, wf2, M2, 4 * D, D, b_trans=True, ldb=4 * D, out=dpp, act=4, act_grad_in=dgg), None, 2 * M2 * 4 * D * D)
@@ -83,6 +91,13 @@ H = 56
 xi = torch.randn(B, H, H, C, device=dev).to(bf)
 gi = torch.randn_like(xi)
 yo = torch.empty_like(xi)
+# stage 1 (28 x 28 x 192)
+xi1 = torch.randn(B, 28, 28, 192, device=dev).to(bf)
+yo1 = torch.empty_like(xi1)
+w491 = torch.randn(49, 192, device=dev)
+bc1 = torch.randn(192, device=dev)
+dw491 = torch.zeros(49, 192, device=dev)
+dbc1 = torch.zeros(192, device=dev)
 w49 = torch.randn(49, C, device=dev)
 bc = torch.randn(C, device=dev)
 dw49 = torch.zeros(49, C, device=dev)
@@ -90,6 +105,8 @@ dbc = torch.zeros(C, device=dev)
 nb = xi.numel() * 2
 bench("dwconv7 fwd                        256x56x56x96", lambda: call("lnx_dwconv7_fwd", xi.data_ptr(), w49.data_ptr(), 0, bc.data_ptr(), None, yo.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
 bench("dwconv7 wgrad                      256x56x56x96", lambda: call("lnx_dwconv7_wgrad", xi.data_ptr(), gi.data_ptr(), dw49.data_ptr(), 0, dbc.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
+bench("dwconv7 fwd                        256x28x28x192", lambda: call("lnx_dwconv7_fwd", xi1.data_ptr(), w491.data_ptr(), 0, bc1.data_ptr(), None, yo1.data_ptr(), B, 28, 28, 192, dt(xi1)), 2 * xi1.numel() * 2, xi1.numel() * 49 * 2)
+bench("dwconv7 wgrad                      256x28x28x192", lambda: call("lnx_dwconv7_wgrad", xi1.data_ptr(), yo1.data_ptr(), dw491.data_ptr(), 0, dbc1.data_ptr(), B, 28, 28, 192, dt(xi1)), 2 * xi1.numel() * 2, xi1.numel() * 49 * 2)
 x2 = xi.view(-1, C)
 g2 = gi.view(-1, C)
 y2d = yo.view(-1, C)
@@ -114,11 +131,14 @@ ab = B * heads * N * hd * 2
 bench("attention fwd                      256x6x200x64", lambda: call("lnx_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr(), B, heads, N, hd, 1, 0), 4 * ab, 2 * 2 * N * N * hd * B * heads)
 bench("attention bwd                      256x6x200x64", lambda: call("lnx_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), ws.data_ptr(), B, heads, N, hd, 1, 0), 8 * ab, 5 * 2 * N * N * hd * B * heads)
 qkv = torch.randn(B, N, 3 * heads * hd, device=dev).to(bf)
+bench("attention fwd from qkv (4-D maps)  256x6x200x64", lambda: call("lnx_attn_qkv_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, heads, N, hd, 1), 4 * ab, 2 * 2 * N * N * hd * B * heads)
+bench("attention bwd from qkv             256x6x200x64", lambda: call("lnx_attn_qkv_bwd", qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, heads, N, hd, 1), 8 * ab, 5 * 2 * N * N * hd * B * heads)
 cos = torch.rand(196, heads, hd // 2, device=dev)
 sin = torch.rand(196, heads, hd // 2, device=dev)
 dqkv = torch.empty_like(qkv)
 dth = torch.zeros(196, heads, hd // 2, device=dev)
 bench("rope fwd (split + cos scale)       256x200x1152", lambda: call("lnx_rope_qk_fwd", qkv.data_ptr(), cos.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), B, N, heads, hd, 4, 0.125, 1), 2 * qkv.numel() * 2)
+bench("rope bwd (scaled q / k input)      256x200x1152", lambda: call("lnx_rope_qk_bwd_scaled", dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), dqkv.data_ptr(), dth.data_ptr(), B, N, heads, hd, 4, 0.125, 1), (2 + 2 / 3) * qkv.numel() * 2)
 bench("rope bwd                           256x200x1152", lambda: call("lnx_rope_qk_bwd", dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), dqkv.data_ptr(), dth.data_ptr(), B, N, heads, hd, 4, 0.125, 1), (2 + 2 / 3) * qkv.numel() * 2)
 
 # ---- optimizer
