@@ -69,7 +69,7 @@ def parse():
 
 # ----------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML every 10 ms; nvidia-smi polling if pynvml is missing)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -77,7 +77,34 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
 
+    def _run_nvml(self) -> bool:
+        """10 ms polling through NVML (same counters nvidia-smi prints); False if pynvml is unusable."""
+        try:
+            import pynvml as N
+
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self._stop.is_set():
+            try:
+                row = [str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx), str(N.nvmlDeviceGetPowerUsage(h) / 1e3), "", "", "", ""]
+                mask = int(get_reasons(h))
+                for bit, col in bits:
+                    row[col] = "Active" if mask & bit else "Not Active"
+                self.rows.append(row)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
