@@ -292,6 +292,15 @@ int lnx_hier_metrics(const void* logits, int dtype, int64_t ld, int B, int K, co
 int lnx_hier_topk(const void* logits, int dtype, int64_t ld, int B, int K, const int* class_off, int kk, int* idx_out, float* prob_out,
                   lnx_stream_t s);
 
+/* Parent / child consistency of the per-rank top-1 predictions, in place on lnx_hier_topk's output (R/inference/postprocessing.py:14-171,
+ * one sample at a time there).  Task 0 = lowest rank, K - 1 = highest.  parent int32 [sum C_k]: parent[class_off[k] + c] = class index,
+ * in task k + 1, of the tree parent of class c of task k (-1: none); null_idx int [K] (host): null class of each task (-1: none).
+ * Walking down from the highest rank, a rank whose parent rank is null, or whose top-1 class is not a child of the parent rank's
+ * (consistent) prediction, becomes the single entry (null class, 1.0): idx[k, b, :] = {null, -1, ...}, prob = {1, 0, ...};
+ * changed uint8 [K, B] (nullable) marks those rows. */
+int lnx_hier_consistency(int* idx, float* prob, const int* parent, const int* class_off, const int* null_idx, unsigned char* changed,
+                         int B, int K, int kk, lnx_stream_t s);
+
 /* ---- batch augmentation feeding the model: the apply step of selective mixup ---- */
 /* out[i, :] = lam * x[i, :] + (1 - lam) * x[perm[i], :]  (fp32 mul, mul, add: bit-equal to the reference expression
  * `lam * v + (1 - lam) * v[perm]`, R/aug/gpu/selective_mixup.py:150,177).  x, out float [B, row] (out != x); perm int64 [B];

@@ -5,7 +5,8 @@ Public surface (mirrors ``linnaeus.models`` / ``linnaeus.loss`` for this path):
 ``weighted_hierarchical_loss``, ``FlatAdamW``, ``DataParallel``, ``install_into_linnaeus``.
 
 Either side of that path, imported on demand: ``linnaeus_b200.aug`` (selective mixup / CutMix feeding the
-model), ``linnaeus_b200.metrics`` (validation metrics, inference top-k), ``linnaeus_b200.gradnorm`` (GradNorm task weighting),
+model), ``linnaeus_b200.metrics`` (validation metrics, inference top-k), ``linnaeus_b200.postprocess`` (hierarchical consistency
+of the predictions), ``linnaeus_b200.gradnorm`` (GradNorm task weighting),
 ``linnaeus_b200.checkpoint`` (checkpoint interchange with the reference).
 """
 from .config import CfgNode, get_default_config, make_synthetic_config, make_synthetic_config_v0  # noqa: F401

@@ -53,6 +53,7 @@ SIGNATURES = {
     "lnx_attn_bias_fwd": [P, P, P, I, I, I, I, F, I, P],
     "lnx_hier_metrics": [P, I, L, I, I, P, P, I, P, P, P],
     "lnx_hier_topk": [P, I, L, I, I, P, I, P, P, P],
+    "lnx_hier_consistency": [P, P, P, P, P, P, I, I, I, P],
     "lnx_mix_pairs": [P, P, P, P, I, L, P],
     "lnx_mix_meta_chunks": [P, P, P, P, P, I, P, P, I, I, P],
     "lnx_cutmix_paste": [P, P, P, P, I, I, I, I, I, I, I, I, P],

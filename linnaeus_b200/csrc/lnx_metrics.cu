@@ -130,6 +130,64 @@ __global__ void __launch_bounds__(128) hier_topk_kernel(const T* __restrict__ lo
 
 }  // namespace
 
+// Parent / child consistency of the per-rank top-1 predictions of a batch, in place on the output of hier_topk_kernel
+// (R/inference/postprocessing.py:14-171, one sample at a time there).  Task 0 is the lowest rank, task K - 1 the highest; thread =
+// sample, walking down from the highest rank: the highest rank is kept; below it, if the parent rank's consistent prediction is its
+// null class, or the tree parent of this rank's top-1 class is not the parent rank's consistent prediction, the rank's prediction
+// list becomes the single entry (null class, probability 1) -- when the rank has a null class; otherwise it is kept as is.
+struct ConsistencyMeta {
+  int off[MAXK + 1];
+  int null_idx[MAXK];  // class index of the null taxon of each task, -1 if the task has none
+};
+__global__ void __launch_bounds__(128) hier_consistency_kernel(int* __restrict__ idx, float* __restrict__ prob, const int* __restrict__ parent,
+                                                               ConsistencyMeta meta, unsigned char* __restrict__ changed, int B, int K, int kk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  int cons = -1;  // consistent class index of the rank above
+  for (int k = K - 1; k >= 0; --k) {
+    int* row = idx + ((long long)k * B + i) * kk;
+    float* prow = prob + ((long long)k * B + i) * kk;
+    const int cur = row[0];
+    bool nullify = false;
+    if (k < K - 1) {
+      const bool parent_is_null = meta.null_idx[k + 1] >= 0 && cons == meta.null_idx[k + 1];
+      if (parent_is_null) {
+        nullify = true;
+      } else {
+        const int C = meta.off[k + 1] - meta.off[k];
+        const int actual = (cur >= 0 && cur < C) ? parent[meta.off[k] + cur] : -1;
+        nullify = actual != cons;
+      }
+    }
+    if (nullify && meta.null_idx[k] >= 0) {
+      row[0] = meta.null_idx[k];
+      prow[0] = 1.0f;
+      for (int t = 1; t < kk; ++t) row[t] = -1, prow[t] = 0.f;
+      cons = meta.null_idx[k];
+      if (changed) changed[(long long)k * B + i] = 1;
+    } else {
+      cons = cur;  // consistent, the highest rank, or a rank that cannot be nullified: its own prediction stands
+      if (changed) changed[(long long)k * B + i] = 0;
+    }
+  }
+}
+
+extern "C" int lnx_hier_consistency(int* idx, float* prob, const int* parent, const int* class_off, const int* null_idx, unsigned char* changed,
+                                    int B, int K, int kk, lnx_stream_t s) {
+  LNX_REQUIRE(idx && prob && parent && class_off && null_idx, LNX_ERR_NULL);
+  LNX_REQUIRE(B > 0 && K > 0 && K <= MAXK && kk > 0, LNX_ERR_SHAPE);
+  ConsistencyMeta meta;
+  for (int k = 0; k <= K; ++k) meta.off[k] = class_off[k];
+  for (int k = 0; k < K; ++k) {
+    LNX_REQUIRE(meta.off[k + 1] > meta.off[k], LNX_ERR_SHAPE);
+    LNX_REQUIRE(null_idx[k] < meta.off[k + 1] - meta.off[k], LNX_ERR_SHAPE);
+    meta.null_idx[k] = null_idx[k];
+  }
+  hier_consistency_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)s>>>(idx, prob, parent, meta, changed, B, K, kk);
+  LNX_CHECK_LAUNCH();
+  return LNX_OK;
+}
+
 extern "C" int lnx_hier_topk(const void* logits, int dtype, int64_t ld, int B, int K, const int* class_off, int kk, int* idx_out,
                              float* prob_out, lnx_stream_t s) {
   LNX_REQUIRE(logits && class_off && idx_out && prob_out, LNX_ERR_NULL);

@@ -78,3 +78,62 @@ print(f"HierMetricsAccumulator.update (host wall, no sync):     {timeit(lambda: 
 print(f"reference call sequence on the same GPU tensors:        {timeit(reference_sequence, 20):.3f} ms per batch ({2 * len(keys) + 3} .item() syncs)")
 print(f"topk_predictions(k=5), one launch + one read-back:      {timeit(lambda: M.topk_predictions(outs, 5), 20):.3f} ms per batch")
 print(f"reference per-sample softmax/topk/.item() loop:         {timeit(reference_topk, 2):.1f} ms per batch")
+
+# ---- hierarchical consistency (postprocessing.py:14-171): batch kernel behind the top-k against the per-sample Python walk
+import numpy as np  # noqa: E402
+
+import linnaeus_b200.postprocess as PP  # noqa: E402
+from linnaeus_b200.config import SyntheticTaxonomy  # noqa: E402
+
+tax = SyntheticTaxonomy({k: c for k, c in zip(keys, classes)})
+
+
+class _Tree:  # the one method the walk needs from a TaxonomyTree
+    task_keys, num_classes = keys, tax.num_classes
+
+    @staticmethod
+    def get_parent(node):
+        t, c = node
+        i = keys.index(t)
+        return (keys[i + 1], tax.parent_of(t, c)) if i + 1 < len(keys) and c != 0 else None
+
+
+parent, poffs = PP.parent_table(_Tree, keys, tax.num_classes)
+parent_rows = [parent[poffs[i]:poffs[i + 1]].tolist() for i in range(len(keys))]
+nulls = [0] * len(keys)
+
+
+def reference_walk(top):
+    """the reference's per-sample loop in class-index space (dict lookups + tuple compares per rank), after the top-k lists exist"""
+    out = []
+    for i in range(B):
+        cons = None
+        row = []
+        for k in range(len(keys) - 1, -1, -1):
+            cur = int(top[keys[k]][0][i, 0])
+            nullify = False
+            if k < len(keys) - 1:
+                if cons == nulls[k + 1]:
+                    nullify = True
+                else:
+                    nullify = parent_rows[k][cur] != cons
+            cons = nulls[k] if nullify else cur
+            row.append((cons, nullify))
+        out.append(row)
+    return out
+
+
+top_cpu = M.topk_predictions(outs, 5)
+t_fused = timeit(lambda: PP.topk_consistent_predictions(outs, parent, poffs, nulls, 5), 20)
+t_walk = timeit(lambda: reference_walk(top_cpu), 5)
+idx_d = torch.zeros((len(keys), B, 5), dtype=torch.int32, device=dev)
+prob_d = torch.rand((len(keys), B, 5), device=dev)
+ch_d = torch.empty((len(keys), B), dtype=torch.uint8, device=dev)
+PP.enforce_consistency_batch(idx_d, prob_d, parent, poffs, nulls, ch_d)
+e0.record()
+for _ in range(100):
+    PP.enforce_consistency_batch(idx_d, prob_d, parent, poffs, nulls, ch_d)
+e1.record()
+torch.cuda.synchronize()
+print(f"topk + hierarchical consistency, 2 launches + 1 read-back: {t_fused:.3f} ms per batch (lnx_hier_consistency alone: {e0.elapsed_time(e1) / 100 * 1e3:.1f} us)")
+print(f"per-sample consistency walk in Python (after the top-k loop): {t_walk:.2f} ms per batch")
