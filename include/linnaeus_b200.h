@@ -185,6 +185,11 @@ int lnx_attn_fwd(const void* q, const void* k, const void* v, void* out, float* 
 int lnx_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const float* lse,
                  void* dq, void* dk, void* dv, float* delta_ws, int B, int heads, int N, int hd, int dtype, int force_simt, lnx_stream_t s);
 
+/* bf16 GEMM on CTA pairs (tcgen05.mma.cta_group::2, 256 x block_n tiles, each CTA stages half of the B tile): c[M, N] = a[M, K] b[N, K]^T
+ * (+ bias).  N % 128 == 0, K % 8 == 0.  The 2-SM building block for the transformer-stage Linear layers (R/models/blocks/mlp.py:37-39,
+ * rope_2d_mhsa.py:292-294). */
+int lnx_gemm_pair(const void* a, const void* b, const float* bias, void* c, int64_t M, int N, int K, lnx_stream_t s);
+
 /* The qkv projection with the cos factors and the softmax scale applied in its epilogue (replaces self.qkv(x) + the q / k scaling of
  * rope_2d_mhsa.py:432-501): qkv[M, 3 D] bf16 = x[M, K] w[3 D, K]^T + bias, q / k columns of the image tokens times
  * cos(tx fx + ty fy) computed from freqs [2, D / 2] (the learnable frequencies, float32) in the epilogue, q columns times q_scale.

@@ -64,6 +64,7 @@ SIGNATURES = {
     "lnx_rope_qk_bwd": [P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, P],
     "lnx_rope_qk_bwd_scaled": [P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, P],
     "lnx_rope_freq_grad": [P, P, I, I, I, I, P],
+    "lnx_gemm_pair": [P, P, P, P, L, I, I, P],
     "lnx_qkv_rope_gemm": [P, P, P, P, P, L, I, I, I, I, I, F, P],
     "lnx_attn_qkv_fwd": [P, P, P, I, I, I, I, I, P],
     "lnx_attn_qkv_bwd": [P, P, P, P, P, P, P, I, I, I, I, I, P],

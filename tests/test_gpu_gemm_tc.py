@@ -114,3 +114,19 @@ def test_wgrad_kernel(M, N, K, with_db):
     assert rel_err(dw, ref) < 2e-5
     if with_db:
         assert rel_err(db, dy.float().sum(0) - 1.0) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(256, 128, 64, True), (1000, 256, 192, True), (4097, 384, 384, False), (12544, 768, 768, True), (300, 1152, 72, True)])
+def test_gemm_on_cta_pairs_matches_fp32_torch(M, N, K, bias):
+    """lnx_gemm_pair: tcgen05.mma.cta_group::2 on 256-row pair tiles (each CTA stages half of the B tile), ragged M, K not a multiple
+    of the 64-wide k-block, block_n 256 and 128."""
+    from linnaeus_b200._lib import call
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    call("lnx_gemm_pair", a.data_ptr(), w.data_ptr(), b.data_ptr() if bias else None, out.data_ptr(), M, N, K)
+    ref = a.float() @ w.float().t() + (b if bias else 0.0)
+    assert float((out.float() - ref).abs().max() / ref.abs().max()) < 8e-3
