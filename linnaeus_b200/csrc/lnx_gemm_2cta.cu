@@ -1,10 +1,10 @@
 // bf16 GEMM on CTA pairs: C[M, N] = A[M, K] B[N, K]^T (+ bias), tcgen05.mma.cta_group::2.
 //
-// Why: with one CTA per tile a 128 x 256 x 16 MMA reads 4 KB of A and 8 KB of B from shared memory for 64 tensor cycles -- more than
-// the 128 B / clk port delivers (profiles/r02_microbench.md: the 1-CTA kernel tops out at 55-65 % of the tensor pipe on the
-// transformer-stage shapes, 10-30 % behind cuBLAS).  A CTA pair computes a 256 x BN tile: each CTA stages its own 128 rows of A and
-// only HALF of the B tile; the pair's tensor cores read the other half from the peer's shared memory.  Per SM and k-step that is
-// 4 + 4 KB of fills instead of 4 + 8, and the B reads are shared.
+// A CTA pair computes a 256 x BN tile: each CTA stages its own 128 rows of A and only HALF of the B tile; the pair's tensor cores read
+// the other half from the peer's shared memory (per SM and k-step 4 + 4 KB of fills instead of 4 + 8).  Measured on the
+// transformer-stage shapes (profiles/r02_microbench.md): same 1.16 PFLOP/s as the 1-CTA kernel where the main loop dominates
+// (K = 3072), slower at K = 384 with this file's plain epilogue -- so the train step does not use it; it is the tested 2-SM building
+// block (cluster launch, 2-SM TMA, multicast commit, pair-allocated TMEM) for cluster-multicast / stream-K work.
 //
 // Structure (persistent, one cluster of 2 CTAs per SM pair; rank 0 = leader):
 //   warp 0  TMA producer (both CTAs): A rows [m0 + 128 rank, +128), B rows [n0 + BN/2 rank, +BN/2) of every k-block into the CTA's own
