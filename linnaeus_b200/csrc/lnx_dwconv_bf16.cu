@@ -90,8 +90,13 @@ __global__ void __launch_bounds__(NTHREADS, NS == 2 ? 3 : 2)
         const int buf = it % NS;
         mbar_wait_relaxed(&empty[buf], (((uint32_t)it / NS) & 1u) ^ 1u);
         const TileCoord tc = tile_coord(t, tiles_w, tiles_h);
+#ifdef LNX_DW_NOLOAD  // profiling ablation (tools/build_variant.sh): no halo loads, the compute warps run on whatever is in shared memory
+        (void)tc;
+        mbar_arrive(&full[buf]);
+#else
         mbar_expect_tx(&full[buf], HALO_BYTES);
         tma_load_4d(tiles + buf * HALO_BYTES, &tmX, &full[buf], c0, tc.w0 - 3, tc.h0 - 3, tc.b);
+#endif
       }
     }
     return;
