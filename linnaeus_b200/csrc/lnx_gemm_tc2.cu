@@ -648,7 +648,8 @@ int lnx_gemm_tc2(const GemmArgs& g, float* colsum_out, cudaStream_t st) {
   // small K: the epilogue is the whole cost -> 4 groups, double staging; large K: deeper operand ring first
   auto fixed_bytes = [&](int groups, int bufs) { return 1024 + 4 * groups * bufs * WARP_STAGE_BYTES + 1024 + (colsum_out ? g.N * 4 : 0); };
   const int want = min(4, 2 * num_kb);
-  p.groups = num_kb <= 4 ? 4 : 2;
+  // the token-factor epilogue (cos-RoPE qkv projection) is heavy enough to want 16 epilogue warps at K = 384 too: 0.074 -> 0.068 ms
+  p.groups = (num_kb <= 4 || (g.tok_scale && num_kb <= 12)) ? 4 : 2;
   p.bufs = 2;
   int stages = (MAX_SMEM - fixed_bytes(p.groups, p.bufs)) / stage_bytes;
   if (stages < want && n_b_users == 0) {
