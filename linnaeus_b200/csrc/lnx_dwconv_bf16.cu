@@ -411,10 +411,19 @@ bool make_nhwc_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C
 
 }  // namespace
 
+// tensor-pipe kernels of lnx_dwconv_mma.cu (LNX_ERR_UNSUPPORTED = shape not covered: use the kernels of this file)
+bool lnx_dwconv7_mma_enabled();
+int lnx_dwconv7_fwd_mma(const void* x, const float* w, int wl, const float* bias, const void* res, void* y, int B, int H, int W, int C, cudaStream_t st);
+int lnx_dwconv7_wgrad_mma(const void* x, const void* dy, float* dw, int wl, float* dbias, int B, int H, int W, int C, cudaStream_t st);
+
 int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, int wl, const float* bias, const void* res, void* y, int B, int H, int W, int C,
                          cudaStream_t st) {
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 7u)) return LNX_ERR_ALIGN;
   if (C % CC != 0) return LNX_ERR_SHAPE;
+  if (lnx_dwconv7_mma_enabled() && lnx_aligned16(res)) {
+    const int rc = lnx_dwconv7_fwd_mma(x, w49c, wl, bias, res, y, B, H, W, C, st);
+    if (rc != LNX_ERR_UNSUPPORTED) return rc;
+  }
   const int chunks = C / CC;
   const int tiles_w = (W + TILE - 1) / TILE;
   // LNX_DWCONV_KERNEL: 4 = four output rows per lane (28 x 14 tiles; measured faster only for large images: used when H >= 64), 2 / 3 = the
@@ -461,6 +470,10 @@ int lnx_dwconv7_fwd_bf16(const void* x, const float* w49c, int wl, const float* 
 
 int lnx_dwconv7_wgrad_bf16(const void* x, const void* dy, float* dw49c, int wl, float* dbias, int B, int H, int W, int C, cudaStream_t st) {
   if (C % CC != 0) return LNX_ERR_SHAPE;
+  if (lnx_dwconv7_mma_enabled()) {
+    const int rc = lnx_dwconv7_wgrad_mma(x, dy, dw49c, wl, dbias, B, H, W, C, st);
+    if (rc != LNX_ERR_UNSUPPORTED) return rc;
+  }
   CUtensorMap tmX, tmG;
   if (!make_nhwc_tmap(&tmX, x, B, H, W, C, HALO, HALO) || !make_nhwc_tmap(&tmG, dy, B, H, W, C, TILE, TILE)) return LNX_ERR_UNSUPPORTED;
   const int tiles_w = (W + TILE - 1) / TILE, tiles_h = (H + TILE - 1) / TILE;
