@@ -120,23 +120,38 @@ __device__ __forceinline__ void item_next(Item& c, int tiles_w, int tiles_h, int
 }
 
 // ------------------------------------------------------------------ forward (and data gradient with flipped taps)
-// One persistent CTA per SM, NW warps.  Work items = (32-channel chunk, image, 16-row x WT-column output tile), chunk-major, a contiguous
-// range per CTA.  The halo tile [22][RP] pixels of the NEXT item is fetched by one 4-D TMA load (hardware zero fill = the conv padding)
-// into the other buffer while the warps compute this one (full / empty mbarriers, no CTA-wide barrier in the steady state); the band
-// table [32][7][11] x 8 B + bias of the chunk is rebuilt only when the chunk changes (at most twice per CTA).
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-    dwconv7_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w, const float* __restrict__ bias,
-                           const bf16* __restrict__ res, bf16* __restrict__ y, int B, int H, int W, int C, int tiles_w, int tiles_h, int WT, int RP,
-                           int nxb, int wl, int tile_bytes, int dbg) {
+// One persistent CTA per SM, 16 warps.  Work items = (32-channel chunk, image, 16-row x WT-column output tile, WT <= 32), chunk-major, a
+// contiguous range per CTA.  Per item: the halo tile [22][RP] pixels arrives by one 4-D TMA load (hardware zero fill = the conv padding)
+// issued one item ahead into the other buffer; every warp computes one (column block, channel group) unit and writes / adds its bf16
+// outputs into a swizzled staging tile [16][WT] x 64 B; the staging tile leaves by ONE 4-D TMA store (whole 64-byte pixel rows, clipped
+// at the image edge by the hardware) issued by thread 0 once every warp has arrived on the item's "done" barrier.  For the data gradient
+// the skip-connection gradient is TMA-loaded INTO the staging tile first and the epilogue adds to it in place.  (Per-thread 16-byte
+// stores straight to global cost 40 % of the kernel: half-written 32-byte sectors.)  The band table [32][7][11] x 8 B + bias of the
+// chunk is rebuilt only when the chunk changes (at most twice per CTA).
+constexpr int FWD_WARPS = 16;
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(FWD_WARPS * 32, 1)
+    dwconv7_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                           const float* __restrict__ w, const float* __restrict__ bias, int has_res, int B, int C, int tiles_w, int tiles_h, int WT,
+                           int RP, int nxb, int wl, int tile_bytes, int out_bytes, int dbg) {
+  constexpr int NW = FWD_WARPS;
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* tiles = smem;  // [2][tile_bytes]
-  uint2* btab = reinterpret_cast<uint2*>(smem + 2 * (size_t)tile_bytes);
-  float* bias_s = reinterpret_cast<float*>(smem + 2 * (size_t)tile_bytes + BTAB_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)tile_bytes + BTAB_BYTES + CC * 4);
-  uint64_t* empty = full + 2;
-  const uint32_t tiles_s = smem_u32(tiles);
-  const uint32_t load_bytes = (uint32_t)(IN_ROWS * RP * 64);
+  unsigned char* tiles = smem;                               // [2][tile_bytes]
+  unsigned char* outs = smem + 2 * (size_t)tile_bytes;       // [2][out_bytes]
+  unsigned char* rest = outs + 2 * (size_t)out_bytes;
+  uint2* btab = reinterpret_cast<uint2*>(rest);
+  float* bias_s = reinterpret_cast<float*>(rest + BTAB_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(rest + BTAB_BYTES + CC * 4);
+  uint64_t* empty = full + 2;    // = "done": every warp has read the halo tile and written its outputs
+  uint64_t* outfree = full + 4;  // the staging tile may be written (its previous TMA store has been read out; the residual has landed)
+  const uint32_t tiles_s = smem_u32(tiles), outs_s = smem_u32(outs);
+  const uint32_t load_bytes = (uint32_t)(IN_ROWS * RP * 64), res_bytes = (uint32_t)(TROWS * WT * 64);
 
   const long long n_items = (long long)B * tiles_w * tiles_h * (C / CC);
   const int it_begin = (int)(n_items * blockIdx.x / gridDim.x), it_end = (int)(n_items * (blockIdx.x + 1) / gridDim.x);
@@ -144,40 +159,56 @@ __global__ void __launch_bounds__(NW * 32, 1)
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
+    prefetch_tmap(&tmY);
+    if (has_res) prefetch_tmap(&tmR);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], NW);
+      mbar_init(&outfree[i], 1);
     }
     mbar_fence_init();
   }
-  // the slack behind each buffer is never written by TMA: it only has to hold finite values (it meets zero band entries)
+  // the slack behind each halo buffer is never written by TMA: it only has to hold finite values (it meets zero band entries)
   for (int i = threadIdx.x; i < 2 * (SLACK_BYTES / 16); i += NW * 32)
     reinterpret_cast<uint4*>(tiles + (size_t)(i / (SLACK_BYTES / 16)) * tile_bytes + load_bytes)[i % (SLACK_BYTES / 16)] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
-  auto issue = [&](int n, const Item& c) {  // thread 0: fetch the halo tile of this CTA's n-th item into buffer n & 1
-    const int buf = n & 1;
-    mbar_wait_relaxed(&empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
-    if (dbg & 1) {
-      mbar_arrive(&full[buf]);
-      return;
-    }
-    mbar_expect_tx(&full[buf], load_bytes);
-    tma_load_4d(tiles + (size_t)buf * tile_bytes, &tmX, &full[buf], c.chunk * CC, c.tw * WT - 3, c.th * TROWS - 3, c.b);
-  };
   Item cur = item_of(it_begin, tiles_w, tiles_h, B);
-  if (threadIdx.x == 0 && n_my > 0) issue(0, cur);
+  Item prev = cur;
+  if (threadIdx.x == 0 && n_my > 0) {
+    mbar_expect_tx(&full[0], load_bytes);
+    tma_load_4d(tiles, &tmX, &full[0], cur.chunk * CC, cur.tw * WT - 3, cur.th * TROWS - 3, cur.b);
+  }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int e = t - g + 7;
   const int hRP = RP >> 1;
   const int P = 2 * g * RP + t;
+  const int nunits = nxb * 4;
   int cur_chunk = -1;
   for (int it = 0; it < n_my; ++it) {
     Item nxt = cur;
     item_next(nxt, tiles_w, tiles_h, B);
-    if (threadIdx.x == 0 && it + 1 < n_my) issue(it + 1, nxt);
-    const int c0 = cur.chunk * CC, y0 = cur.th * TROWS, x0 = cur.tw * WT, b = cur.b;
+    const int buf = it & 1;
+    if (threadIdx.x == 0) {
+      if (it >= 1) {  // item it-1 is complete in its staging tile: send it off
+        mbar_wait_relaxed(&empty[buf ^ 1], (((uint32_t)(it - 1)) >> 1) & 1u);
+        if (!(dbg & 2)) tma_store_4d(&tmY, outs + (size_t)(buf ^ 1) * out_bytes, prev.chunk * CC, prev.tw * WT, prev.th * TROWS, prev.b);
+        bulk_commit_group();
+      }
+      if (it + 1 < n_my) {  // halo tile of the next item into the buffer item it-1 has just released
+        mbar_expect_tx(&full[buf ^ 1], load_bytes);
+        tma_load_4d(tiles + (size_t)(buf ^ 1) * tile_bytes, &tmX, &full[buf ^ 1], nxt.chunk * CC, nxt.tw * WT - 3, nxt.th * TROWS - 3, nxt.b);
+      }
+      if (it >= 1) bulk_wait_group_read<1>();  // the store of item it-2 has left this item's staging tile
+      if (has_res) {
+        mbar_expect_tx(&outfree[buf], res_bytes);
+        tma_load_4d(outs + (size_t)buf * out_bytes, &tmR, &outfree[buf], cur.chunk * CC, cur.tw * WT, cur.th * TROWS, cur.b);
+      } else {
+        mbar_arrive(&outfree[buf]);
+      }
+    }
+    const int c0 = cur.chunk * CC;
     if (cur.chunk != cur_chunk) {  // uniform over the CTA
       cur_chunk = cur.chunk;
       __syncthreads();  // every warp is done with the previous chunk's table
@@ -196,14 +227,14 @@ __global__ void __launch_bounds__(NW * 32, 1)
       if (threadIdx.x < CC) bias_s[threadIdx.x] = bias ? bias[c0 + threadIdx.x] : 0.f;
       __syncthreads();
     }
+    prev = cur;
     cur = nxt;
-    const int buf = it & 1;
-    mbar_wait(&full[buf], ((uint32_t)it >> 1) & 1u);
+    const uint32_t par = ((uint32_t)it >> 1) & 1u;
+    mbar_wait(&full[buf], par);
     const uint32_t tile_s = tiles_s + (uint32_t)buf * (uint32_t)tile_bytes;
-    const int xlim = min(W, x0 + WT);
+    const uint32_t out_s = outs_s + (uint32_t)buf * (uint32_t)out_bytes;
 
-    if (!(dbg & 4))
-    for (int u = warp; u < nxb * 4; u += NW) {
+    for (int u = warp; u < nunits; u += NW) {
       const int j = u % nxb, cg = u / nxb;
       float acc[8][4];
 #pragma unroll
@@ -237,27 +268,20 @@ __global__ void __launch_bounds__(NW * 32, 1)
           phi[ch] = chi[ch];
         }
       }
-      if (dbg & 2) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) sacc += acc[ch][0] + acc[ch][1] + acc[ch][2] + acc[ch][3];
-        if (sacc == 1.2345f) y[0] = __float2bfloat16_rn(sacc);
-        continue;
-      }
-      // thread (g, t): rows 2g, 2g+1 x columns 8j+2t, 8j+2t+1 x 8 channels = four 16-byte stores
-      const int yy0 = y0 + 2 * g, xc0 = x0 + 8 * j + 2 * t;
-      const long long off0 = (((long long)b * H + yy0) * W + xc0) * C + c0 + cg * 8;
+      // thread (g, t): rows 2g, 2g+1 x columns 8j+2t, 8j+2t+1 x 8 channels = four 16-byte chunks of the staging tile
+      mbar_wait(&outfree[buf], par);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
         for (int xx = 0; xx < 2; ++xx) {
-          if (yy0 + hh < H && xc0 + xx < xlim) {
-            const long long off = off0 + (long long)(hh * W + xx) * C;
+          const int xl = 8 * j + 2 * t + xx;
+          if (xl < WT) {
+            const uint32_t addr = out_s + swz((2 * g + hh) * WT + xl, cg);
             float v[8];
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) v[ch] = acc[ch][2 * hh + xx];
-            if (res) {  // fused "+ residual" (the skip-connection gradient when this kernel runs as the data gradient)
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res + off));
+            if (has_res) {  // fused "+ residual" (the skip-connection gradient when this kernel runs as the data gradient)
+              const uint4 rv = lds128<0>(addr);
               const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -265,13 +289,23 @@ __global__ void __launch_bounds__(NW * 32, 1)
                 v[2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
               }
             }
-            *reinterpret_cast<uint4*>(y + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])),
+                         "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+                         : "memory");
           }
         }
       }
     }
+    fence_proxy_async_smem();  // this thread's staging writes become visible to the TMA store
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[buf]);
+  }
+  if (threadIdx.x == 0 && n_my > 0) {
+    const int lb = (n_my - 1) & 1;
+    mbar_wait_relaxed(&empty[lb], (((uint32_t)(n_my - 1)) >> 1) & 1u);
+    if (!(dbg & 2)) tma_store_4d(&tmY, outs + (size_t)lb * out_bytes, prev.chunk * CC, prev.tw * WT, prev.th * TROWS, prev.b);
+    bulk_commit_group();
+    bulk_wait_group_all();
   }
 }
 
@@ -432,33 +466,29 @@ bool lnx_dwconv7_mma_enabled() {
 int lnx_dwconv7_fwd_mma(const void* x, const float* w, int wl, const float* bias, const void* res, void* y, int B, int H, int W, int C,
                         cudaStream_t st) {
   if (C % CC != 0) return LNX_ERR_SHAPE;
-  const int tiles_w = (W + 55) / 56;
-  const int WT = tiles_w == 1 ? W : ((W + tiles_w - 1) / tiles_w + 7) / 8 * 8;
+  const int tiles_w = (W + 31) / 32;
+  const int WT = tiles_w == 1 ? W : ((W + tiles_w - 1) / tiles_w + 3) / 4 * 4;
   const int RP = round_up_mod(WT + 6, 4, 2);  // 2 mod 4: two tile rows apart = 4 pixels mod 8 (bank-conflict-free quads)
   const int nxb = (WT + 7) / 8;
   const int tiles_h = (H + TROWS - 1) / TROWS;
   const int tile_bytes = (IN_ROWS * RP * 64 + SLACK_BYTES + 1023) / 1024 * 1024;
-  const size_t smem = 2 * (size_t)tile_bytes + BTAB_BYTES + CC * 4 + 64;
-  if (smem > kMaxSmem || RP > 256) return LNX_ERR_UNSUPPORTED;
-  CUtensorMap tmX;
-  if (!make_nhwc_sw64_tmap(&tmX, x, B, H, W, C, RP, IN_ROWS)) return LNX_ERR_UNSUPPORTED;
+  const int out_bytes = (TROWS * WT * 64 + 1023) / 1024 * 1024;
+  const size_t smem = 2 * (size_t)tile_bytes + 2 * (size_t)out_bytes + BTAB_BYTES + CC * 4 + 64;
+  if (smem > kMaxSmem) return LNX_ERR_UNSUPPORTED;
+  CUtensorMap tmX, tmY, tmR;
+  if (!make_nhwc_sw64_tmap(&tmX, x, B, H, W, C, RP, IN_ROWS) || !make_nhwc_sw64_tmap(&tmY, y, B, H, W, C, WT, TROWS)) return LNX_ERR_UNSUPPORTED;
+  if (!make_nhwc_sw64_tmap(&tmR, res ? res : y, B, H, W, C, WT, TROWS)) return LNX_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv7_fwd_mma_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv7_fwd_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    cudaError_t e = cudaFuncSetAttribute(dwconv7_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     if (e != cudaSuccess) return lnx_set_cuda_error(e);
     attr_set = true;
   }
-  static const int dbg = getenv("LNX_DW_DBG") ? atoi(getenv("LNX_DW_DBG")) : 0;  // profiling ablations: 1 no loads, 2 no stores, 4 no compute
+  static const int dbg = getenv("LNX_DW_DBG") ? atoi(getenv("LNX_DW_DBG")) : 0;  // profiling ablation: 2 = no output stores
   const long long n_items = (long long)B * tiles_h * tiles_w * (C / CC);
   const int grid = (int)(n_items < kNumSMs ? n_items : kNumSMs);
-  const int nunits = nxb * 4;
-  // 14 or 16 warps, whichever wastes fewer warp slots on the (column block, channel group) units of a tile
-  const int waste14 = (nunits + 13) / 14 * 14 - nunits, waste16 = (nunits + 15) / 16 * 16 - nunits;
-  if (waste14 * 16 < waste16 * 14)
-    dwconv7_fwd_mma_kernel<14><<<grid, 14 * 32, smem, st>>>(tmX, w, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h, WT, RP, nxb, wl, tile_bytes, dbg);
-  else
-    dwconv7_fwd_mma_kernel<16><<<grid, 16 * 32, smem, st>>>(tmX, w, bias, (const bf16*)res, (bf16*)y, B, H, W, C, tiles_w, tiles_h, WT, RP, nxb, wl, tile_bytes, dbg);
+  dwconv7_fwd_mma_kernel<<<grid, FWD_WARPS * 32, smem, st>>>(tmX, tmY, tmR, w, bias, res ? 1 : 0, B, C, tiles_w, tiles_h, WT, RP, nxb, wl, tile_bytes,
+                                                             out_bytes, dbg);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
