@@ -22,7 +22,8 @@
 // Weight gradient, one channel, TWO padded input rows yi, yi + 1 and 16 output columns per MMA:
 //     A[m = kx][k = x] = in_h[yi][x + kx]  (rows 8..15: the same for row yi + 1),   B[k = x][n] = dy[yi - n][x]  (n = 7: dy[yi + 1][x])
 //     D[kx][n]      -> dW[ky = n][kx]      (n <= 6),        D[8 + kx][n] -> dW[ky = n + 1][kx] (n <= 5),  D[8 + kx][7] -> dW[0][kx]
-// i.e. all 49 taps of both input rows (98 of 128 outputs useful); row m = 7 of A is all ones, so D[7][0] + D[7][7] = the bias gradient.
+// i.e. all 49 taps of both input rows (98 of 128 outputs useful); row m = 7 of A is all ones, so D[7][2] + D[7][3] (dy rows yi - 2, yi - 3 = the
+// image rows under the two padded input rows, which are stepped over the image rows only) = the bias gradient.
 // Accumulators stay in registers across every tile a persistent CTA visits.
 #include <stdlib.h>
 
@@ -40,8 +41,8 @@ constexpr int IN_ROWS = TROWS + 6;
 constexpr int BTAB_ENTRIES = CC * 7 * 11;
 constexpr int BTAB_BYTES = BTAB_ENTRIES * 8;  // 19712
 constexpr int SLACK_BYTES = 1024;             // 16 pixels behind a tile: the K windows of the last column block end there
-constexpr int WG_ROWS = 8;        // weight gradient: padded input rows per band (4 row pairs)
-constexpr int WG_GROWS = WG_ROWS + 6;
+// weight gradient: padded input rows per band = 8 (4 row pairs, one per warp quarter) or, when two stages of the wider band still fit in
+// shared memory (W <= 28), 16 (two row pairs per warp: half the per-item overhead, 22 / 16 instead of 14 / 8 dy rows fetched per band)
 constexpr int WG_RED_BYTES = 50 * CC * 4;  // 6400
 constexpr int WG_WARPS = 16;
 
@@ -329,7 +330,7 @@ __device__ __forceinline__ void wgrad_flush(float (&acc)[8][4], float* red, floa
         if (n <= 6) atomicAdd(&red[(n * 7 + g) * CC + c], acc[ch][q]);           // dW[ky = n][kx = g] from row yi
         if (n <= 5) atomicAdd(&red[((n + 1) * 7 + g) * CC + c], acc[ch][2 + q]);  // dW[ky = n + 1][kx = g] from row yi + 1
         if (n == 7) atomicAdd(&red[g * CC + c], acc[ch][2 + q]);                  // dW[0][kx = g] from row yi + 1
-      } else if (n == 0 || n == 7) {
+      } else if (n == 2 || n == 3) {  // row of ones x dy rows yi - 3, yi - 2 = the two IMAGE rows of this row pair: every dy row exactly once
         atomicAdd(&red[49 * CC + c], acc[ch][q]);
       }
     }
@@ -345,14 +346,14 @@ __device__ __forceinline__ void wgrad_flush(float (&acc)[8][4], float* red, floa
 __global__ void __launch_bounds__(WG_WARPS * 32, 1)
     dwconv7_wgrad_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, float* __restrict__ dw,
                              float* __restrict__ dbias, int B, int H, int W, int C, int tiles_h, int RP, int RPG, int nxc, int wl, int in_bytes,
-                             int g_bytes) {
+                             int g_bytes, int band_rows) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int stage_bytes = in_bytes + g_bytes;
   float* red = reinterpret_cast<float*>(smem + 2 * (size_t)stage_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)stage_bytes + WG_RED_BYTES);
   uint64_t* empty = full + 2;
   const uint32_t smem_s = smem_u32(smem);
-  const uint32_t in_load = (uint32_t)(WG_ROWS * RP * 64), g_load = (uint32_t)(WG_GROWS * RPG * 64);
+  const uint32_t in_load = (uint32_t)(band_rows * RP * 64), g_load = (uint32_t)((band_rows + 6) * RPG * 64);
   constexpr int NT = WG_WARPS * 32;
 
   const long long n_items = (long long)B * tiles_h * (C / CC);
@@ -373,23 +374,25 @@ __global__ void __launch_bounds__(WG_WARPS * 32, 1)
   __syncthreads();
 
   auto issue = [&](int n, const Item& c) {  // c.th = band index, c.tw unused
-    const int yi0 = c.th * WG_ROWS;  // first padded input row of the band
+    const int y0 = c.th * band_rows;  // first IMAGE row of the input band (= padded row y0 + 3: the all-zero padding rows above / below the
+                                      // image are never visited); the dy band starts six padded rows = three image rows higher
     const int buf = n & 1;
     unsigned char* st = smem + (size_t)buf * stage_bytes;
     mbar_wait_relaxed(&empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
     mbar_expect_tx(&full[buf], in_load + g_load);
-    tma_load_4d(st, &tmX, &full[buf], c.chunk * CC, -3, yi0 - 3, c.b);
-    tma_load_4d(st + in_bytes, &tmG, &full[buf], c.chunk * CC, 0, yi0 - 6, c.b);
+    tma_load_4d(st, &tmX, &full[buf], c.chunk * CC, -3, y0, c.b);
+    tma_load_4d(st + in_bytes, &tmG, &full[buf], c.chunk * CC, 0, y0 - 3, c.b);
   };
   Item cur = item_of(it_begin, 1, tiles_h, B);
   if (threadIdx.x == 0 && n_my > 0) issue(0, cur);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int cg = warp & 3, rp = warp >> 2;
-  // per-lane byte offsets inside a stage (the swizzle term does not change when the column advances by 16 pixels)
+  // per-lane byte offsets inside a stage of the warp's first row pair (the swizzle term does not change when the column advances by 16
+  // pixels; the second row pair of a 16-row band lies 8 tile rows further down)
   const int pa0 = (2 * rp) * RP + t + g, pa1 = pa0 + RP;
   const int pb = ((g < 7) ? (2 * rp + 6 - g) : (2 * rp + 7)) * RPG + t;
-  const uint32_t oa0 = swz(pa0, cg), oa1 = swz(pa1, cg), ob = (uint32_t)in_bytes + swz(pb, cg);
+  const int nrp = band_rows / 8;
 
   float acc[8][4];
 #pragma unroll
@@ -409,30 +412,35 @@ __global__ void __launch_bounds__(WG_WARPS * 32, 1)
     mbar_wait(&full[buf], ((uint32_t)it >> 1) & 1u);
     const uint32_t st = smem_s + (uint32_t)buf * (uint32_t)stage_bytes;
 #pragma unroll 1
-    for (int xc = 0; xc < nxc; ++xc) {
-      const uint32_t xo = (uint32_t)xc * 1024u;
-      uint32_t a0[8], a1[8], a2[8], a3[8], b0[8], b1[8];
-      {
-        const Quad q = lds_quad(st + oa0 + xo);
-        planar8(q.q0, q.q1, a0);
-        planar8(q.q2, q.q3, a2);
-      }
-      {
-        const Quad q = lds_quad(st + oa1 + xo);
-        planar8(q.q0, q.q1, a1);
-        planar8(q.q2, q.q3, a3);
-      }
-      {
-        const Quad q = lds_quad(st + ob + xo);
-        planar8(q.q0, q.q1, b0);
-        planar8(q.q2, q.q3, b1);
-      }
-      if (g == 7) {  // row m = 7 of A: ones -> column sums of dy (bias gradient)
+    for (int k = 0; k < nrp; ++k) {
+      const uint32_t oa0 = st + swz(pa0 + 8 * k * RP, cg), oa1 = st + swz(pa1 + 8 * k * RP, cg);
+      const uint32_t ob = st + (uint32_t)in_bytes + swz(pb + 8 * k * RPG, cg);
+#pragma unroll 1
+      for (int xc = 0; xc < nxc; ++xc) {
+        const uint32_t xo = (uint32_t)xc * 1024u;
+        uint32_t a0[8], a1[8], a2[8], a3[8], b0[8], b1[8];
+        {
+          const Quad q = lds_quad(oa0 + xo);
+          planar8(q.q0, q.q1, a0);
+          planar8(q.q2, q.q3, a2);
+        }
+        {
+          const Quad q = lds_quad(oa1 + xo);
+          planar8(q.q0, q.q1, a1);
+          planar8(q.q2, q.q3, a3);
+        }
+        {
+          const Quad q = lds_quad(ob + xo);
+          planar8(q.q0, q.q1, b0);
+          planar8(q.q2, q.q3, b1);
+        }
+        if (g == 7) {  // row m = 7 of A: ones -> column sums of dy (bias gradient)
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) a0[ch] = a2[ch] = 0x3F803F80u;
-      }
+          for (int ch = 0; ch < 8; ++ch) a0[ch] = a2[ch] = 0x3F803F80u;
+        }
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) mma16816(acc[ch], a0[ch], a1[ch], a2[ch], a3[ch], b0[ch], b1[ch]);
+        for (int ch = 0; ch < 8; ++ch) mma16816(acc[ch], a0[ch], a1[ch], a2[ch], a3[ch], b0[ch], b1[ch]);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[buf]);
@@ -499,13 +507,19 @@ int lnx_dwconv7_wgrad_mma(const void* x, const void* dy, float* dw, int wl, floa
   const int nxc = (W + 15) / 16;
   const int RP = W + 6;
   const int RPG = round_up_mod(16 * nxc, 8, 4);  // 4 mod 8: neighbouring dy rows = the other four pixels mod 8
-  const int tiles_h = (H + 6 + WG_ROWS - 1) / WG_ROWS;
-  const int in_bytes = (WG_ROWS * RP * 64 + SLACK_BYTES + 511) / 512 * 512;
-  const int g_bytes = (WG_GROWS * RPG * 64 + 511) / 512 * 512;
-  const size_t smem = 2 * (size_t)(in_bytes + g_bytes) + WG_RED_BYTES + 64;
+  // bands of 16 input rows when two stages of them fit in shared memory and they waste no more rows than bands of 8
+  int band_rows = ((H + 15) / 16 * 16 <= (H + 7) / 8 * 8) ? 16 : 8, in_bytes = 0, g_bytes = 0;
+  size_t smem = 0;
+  for (;; band_rows = 8) {
+    in_bytes = (band_rows * RP * 64 + SLACK_BYTES + 511) / 512 * 512;
+    g_bytes = ((band_rows + 6) * RPG * 64 + 511) / 512 * 512;
+    smem = 2 * (size_t)(in_bytes + g_bytes) + WG_RED_BYTES + 64;
+    if (smem <= kMaxSmem || band_rows == 8) break;
+  }
   if (smem > kMaxSmem) return LNX_ERR_UNSUPPORTED;
+  const int tiles_h = (H + band_rows - 1) / band_rows;  // bands cover the image rows only
   CUtensorMap tmX, tmG;
-  if (!make_nhwc_sw64_tmap(&tmX, x, B, H, W, C, RP, WG_ROWS) || !make_nhwc_sw64_tmap(&tmG, dy, B, H, W, C, RPG, WG_GROWS)) return LNX_ERR_UNSUPPORTED;
+  if (!make_nhwc_sw64_tmap(&tmX, x, B, H, W, C, RP, band_rows) || !make_nhwc_sw64_tmap(&tmG, dy, B, H, W, C, RPG, band_rows + 6)) return LNX_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(dwconv7_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
@@ -514,7 +528,7 @@ int lnx_dwconv7_wgrad_mma(const void* x, const void* dy, float* dw, int wl, floa
   }
   const long long n_items = (long long)B * tiles_h * (C / CC);
   const int grid = (int)(n_items < kNumSMs ? n_items : kNumSMs);
-  dwconv7_wgrad_mma_kernel<<<grid, WG_WARPS * 32, smem, st>>>(tmX, tmG, dw, dbias, B, H, W, C, tiles_h, RP, RPG, nxc, wl, in_bytes, g_bytes);
+  dwconv7_wgrad_mma_kernel<<<grid, WG_WARPS * 32, smem, st>>>(tmX, tmG, dw, dbias, B, H, W, C, tiles_h, RP, RPG, nxc, wl, in_bytes, g_bytes, band_rows);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
 }
