@@ -104,6 +104,11 @@ int lnx_dwconv7_fwd(const void* x, const float* w, int w_layout, const float* bi
  * gradient buffer), dbias[C] += */
 int lnx_dwconv7_wgrad(const void* x, const void* dy, float* dw, int w_layout, float* dbias, int B, int H, int W, int C, int dtype,
                       lnx_stream_t s);
+/* Which bf16 kernels the two calls above run: 1 = tensor pipe (banded matrix products on mma.sync, lnx_dwconv_mma.cu; the default),
+ * 0 = fp32x2 FMA kernels (lnx_dwconv_bf16.cu; also the fallback for shapes the tensor-pipe kernels do not cover), -1 = back to the
+ * default / the LNX_DWCONV_MMA environment variable.  Returns the previous setting.  For A/B measurements and parity tests of one
+ * implementation against the other; no reference counterpart. */
+int lnx_dwconv7_set_impl(int impl);
 
 /* ---- GEMM with fused epilogue ------------------------------------------ */
 /* Weight (+ bias) gradient of y = x W^T + b on the tensor cores, reduction over the M rows (tokens):

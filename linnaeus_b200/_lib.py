@@ -40,6 +40,7 @@ SIGNATURES = {
     "lnx_layernorm_bwd": [P, P, P, P, P, P, P, P, P, L, I, I, P],
     "lnx_dwconv7_fwd": [P, P, I, P, P, P, I, I, I, I, I, P],
     "lnx_dwconv7_wgrad": [P, P, P, I, P, I, I, I, I, I, P],
+    "lnx_dwconv7_set_impl": [I],
     "lnx_gemm": [I, P, L, I, P, L, I, P, I, I, I, I, P, I, P, P, P, P, P, I, P, I, I, P],
     "lnx_wgrad": [P, L, P, L, P, P, L, I, I, I, P],
     "lnx_mlp_fused_fwd": [P, P, P, P, P, P, P, I, P, P, L, I, I, P],

@@ -465,9 +465,17 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 }  // namespace
 
+static int g_dwconv_impl = -1;  // -1: LNX_DWCONV_MMA or the default (tensor pipe)
+
 bool lnx_dwconv7_mma_enabled() {
-  static const int en = getenv("LNX_DWCONV_MMA") ? atoi(getenv("LNX_DWCONV_MMA")) : 1;
-  return en != 0;
+  static const int env = getenv("LNX_DWCONV_MMA") ? atoi(getenv("LNX_DWCONV_MMA")) : 1;
+  return (g_dwconv_impl < 0 ? env : g_dwconv_impl) != 0;
+}
+
+extern "C" int lnx_dwconv7_set_impl(int impl) {
+  const int prev = g_dwconv_impl;
+  g_dwconv_impl = impl < 0 ? -1 : (impl ? 1 : 0);
+  return prev;
 }
 
 // -> LNX_OK, or LNX_ERR_UNSUPPORTED when the caller should use the FFMA2 kernels

@@ -122,8 +122,9 @@ def test_bf16_mode_matches_reference_golden(name):
 #                   which moves whole rows of these small gradients (measured up to 1.4e-1 relative L2 at B = 2..32)
 #  *.attn.freqs     [2, heads, 32] rotary frequencies: the gradient is a sum over all tokens of products of small differences
 #                   (measured up to 3.0e-2)
-#  aggregate.weight two scalars (measured 3.4e-2 on xl384_shallow)
-BF16_GRAD_ALLOW = (("meta_", 2e-1), (".attn.freqs", 4e-2), ("aggregate.weight", 4e-2))
+#  aggregate.weight two scalars (measured 3.4e-2 on xl384_shallow; 4.03e-2 on tiny_ce once the depthwise convolutions multiply bf16
+#                   weights on the tensor pipe, as the reference's autocast Conv2d does: 3.97e-2 with the fp32-weight FMA kernels)
+BF16_GRAD_ALLOW = (("meta_", 2e-1), (".attn.freqs", 4e-2), ("aggregate.weight", 5e-2))
 
 
 @pytest.mark.parametrize("name", BF16_CASES)

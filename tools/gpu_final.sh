@@ -2,7 +2,7 @@
 # Round-end validation: every GPU test file, smoke(), the default bench (with CPU baseline), the reference arm, inference and
 # V0 benches, the metrics measurement.
 mkdir -p gpurun_out
-bash tools/run_gpu_checks.sh tests/test_gpu_ops.py tests/test_gpu_gemm_tc.py tests/test_gpu_attn_tc.py tests/test_gpu_droppath.py tests/test_gpu_model.py tests/test_gpu_v0.py tests/test_gpu_metrics.py tests/test_gpu_aug.py tests/test_gpu_bench_shapes.py tests/test_gpu_loss_semantics.py tests/test_gpu_mlp_fused.py tests/test_gpu_qkv_rope.py tests/test_gpu_postprocess.py 2>&1 | grep -E "exit|passed|failed|Error|error"
+bash tools/run_gpu_checks.sh tests/test_gpu_ops.py tests/test_gpu_gemm_tc.py tests/test_gpu_attn_tc.py tests/test_gpu_droppath.py tests/test_gpu_model.py tests/test_gpu_v0.py tests/test_gpu_metrics.py tests/test_gpu_aug.py tests/test_gpu_bench_shapes.py tests/test_gpu_loss_semantics.py tests/test_gpu_mlp_fused.py tests/test_gpu_qkv_rope.py tests/test_gpu_postprocess.py tests/test_gpu_dwconv_mma.py 2>&1 | grep -E "exit|passed|failed|Error|error"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; echo "smoke rc $?"; tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "default bench rc $?"; tail -1 gpurun_out/bench_default.log
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log 2>&1; echo "reference rc $?"; tail -1 gpurun_out/bench_reference.log
