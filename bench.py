@@ -34,9 +34,11 @@ FWD_GFLOP = {"sm": 8.659, "md": 12.505, "xl": 448.16}  # per image (SURVEY.md se
 FWD_GFLOP_V0 = {"sm": 8.94}
 FMA_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # fp32 FMA pipe: 148 SMs x 128 lanes x 2 flop at 1965 MHz (no measured figure)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/ (bf16, B = 256 shapes)
+DW_FWD_TRAFFIC, DW_DGRAD_TRAFFIC, DW_WGRAD_TRAFFIC = 157.2e6 + 135.5e6, 312.6e6 + 143.8e6, 311.1e6 + 5.9e6  # rows 32-37 of r02_kernels_summary.md
 NCU_TRAFFIC_BYTES = {  # profiles/r02_kernels_summary.md (read + write)
-    "dwconv7_fwd_x2_kernel 256x56x56x96 (forward; the data gradient is the same kernel + fused skip)": 283.2e6 + 133.8e6,
-    "dwconv7_wgrad_x2_kernel 256x56x56x96": 426.2e6 + 4.8e6,
+    "dwconv7_fwd_mma_kernel 256x56x56x96 (forward)": DW_FWD_TRAFFIC,
+    "dwconv7_fwd_mma_kernel 256x56x56x96 (data gradient + fused skip gradient)": DW_DGRAD_TRAFFIC,
+    "dwconv7_wgrad_mma_kernel 256x56x56x96": DW_WGRAD_TRAFFIC,
     "mlp_fused_fwd_kernel C=96 M=802816": 308.5e6 + 126.1e6,
     "mlp_fused_bwd_kernel C=96 M=802816": 308.5e6 + 1335.0e6,
     "wgrad_tc_kernel dW1 384x96 K=802816": 771.0e6 + 4.2e6,
@@ -528,12 +530,18 @@ def roofline_table(cx: Ctx, B: int, step_ms: float, hbm: float, tf_sus: float):
     dw = torch.zeros(49, C0, device=dev)
     db = torch.zeros(C0, device=dev)
     conv_flops = 2.0 * 49 * M0 * C0
-    add(f"dwconv7_fwd_x2_kernel {B}x56x56x96 (forward; the data gradient is the same kernel + fused skip)",
-        lambda: cx.lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), 0, bias.data_ptr(), None, y.data_ptr(), B, 56, 56, C0, 1), 6, "fp32-fma",
-        alg_bytes=2 * M0 * C0 * 2, flops=conv_flops)
-    add(f"dwconv7_wgrad_x2_kernel {B}x56x56x96",
-        lambda: cx.lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), 0, db.data_ptr(), B, 56, 56, C0, 1), 3, "fp32-fma",
-        alg_bytes=2 * M0 * C0 * 2, flops=conv_flops)
+    dw_note = ("banded matrix products on mma.sync (tensor pipe); bounded by HBM in the limit (49 MAC per 4 bytes is below the tensor ridge), "
+               "measured limiters: shared-memory wavefronts and issue slots of the register-level NHWC -> channel-planar transposition, "
+               "see profiles/r02_dwconv_mma.md")
+    add(f"dwconv7_fwd_mma_kernel {B}x56x56x96 (forward)",
+        lambda: cx.lib.call("lnx_dwconv7_fwd", x.data_ptr(), w49.data_ptr(), 0, bias.data_ptr(), None, y.data_ptr(), B, 56, 56, C0, 1), 3, "hbm",
+        alg_bytes=2 * M0 * C0 * 2, flops=conv_flops, note=dw_note)
+    add(f"dwconv7_fwd_mma_kernel {B}x56x56x96 (data gradient + fused skip gradient)",
+        lambda: cx.lib.call("lnx_dwconv7_fwd", g.data_ptr(), w49.data_ptr(), 0, None, x.data_ptr(), y.data_ptr(), B, 56, 56, C0, 1), 3, "hbm",
+        alg_bytes=3 * M0 * C0 * 2, flops=conv_flops, note=dw_note)
+    add(f"dwconv7_wgrad_mma_kernel {B}x56x56x96",
+        lambda: cx.lib.call("lnx_dwconv7_wgrad", x.data_ptr(), g.data_ptr(), dw.data_ptr(), 0, db.data_ptr(), B, 56, 56, C0, 1), 3, "hbm",
+        alg_bytes=2 * M0 * C0 * 2, flops=conv_flops, note=dw_note)
     # ---- stage 0: fused pointwise pair
     x2 = x.view(M0, C0)
     g2 = g.view(M0, C0)

@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import linnaeus_b200.functional as F
+from linnaeus_b200 import _lib
 from linnaeus_b200._lib import call, dt
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
@@ -103,8 +104,13 @@ bc = torch.randn(C, device=dev)
 dw49 = torch.zeros(49, C, device=dev)
 dbc = torch.zeros(C, device=dev)
 nb = xi.numel() * 2
-bench("dwconv7 fwd                        256x56x56x96", lambda: call("lnx_dwconv7_fwd", xi.data_ptr(), w49.data_ptr(), 0, bc.data_ptr(), None, yo.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
-bench("dwconv7 wgrad                      256x56x56x96", lambda: call("lnx_dwconv7_wgrad", xi.data_ptr(), gi.data_ptr(), dw49.data_ptr(), 0, dbc.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
+bench("dwconv7 fwd (tensor pipe)           256x56x56x96", lambda: call("lnx_dwconv7_fwd", xi.data_ptr(), w49.data_ptr(), 0, bc.data_ptr(), None, yo.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
+bench("dwconv7 dgrad + skip (tensor pipe)  256x56x56x96", lambda: call("lnx_dwconv7_fwd", gi.data_ptr(), w49.data_ptr(), 0, None, xi.data_ptr(), yo.data_ptr(), B, H, H, C, dt(xi)), 3 * nb, xi.numel() * 49 * 2)
+bench("dwconv7 wgrad (tensor pipe)         256x56x56x96", lambda: call("lnx_dwconv7_wgrad", xi.data_ptr(), gi.data_ptr(), dw49.data_ptr(), 0, dbc.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
+_lib.load().lnx_dwconv7_set_impl(0)
+bench("dwconv7 fwd (FFMA2 kernels)         256x56x56x96", lambda: call("lnx_dwconv7_fwd", xi.data_ptr(), w49.data_ptr(), 0, bc.data_ptr(), None, yo.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
+bench("dwconv7 wgrad (FFMA2 kernels)       256x56x56x96", lambda: call("lnx_dwconv7_wgrad", xi.data_ptr(), gi.data_ptr(), dw49.data_ptr(), 0, dbc.data_ptr(), B, H, H, C, dt(xi)), 2 * nb, xi.numel() * 49 * 2)
+_lib.load().lnx_dwconv7_set_impl(-1)
 bench("dwconv7 fwd                        256x28x28x192", lambda: call("lnx_dwconv7_fwd", xi1.data_ptr(), w491.data_ptr(), 0, bc1.data_ptr(), None, yo1.data_ptr(), B, 28, 28, 192, dt(xi1)), 2 * xi1.numel() * 2, xi1.numel() * 49 * 2)
 bench("dwconv7 wgrad                      256x28x28x192", lambda: call("lnx_dwconv7_wgrad", xi1.data_ptr(), yo1.data_ptr(), dw491.data_ptr(), 0, dbc1.data_ptr(), B, 28, 28, 192, dt(xi1)), 2 * xi1.numel() * 2, xi1.numel() * 49 * 2)
 x2 = xi.view(-1, C)

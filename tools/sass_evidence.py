@@ -8,7 +8,7 @@ import sys
 LIB = "linnaeus_b200/liblinnaeus_b200.so"
 keep = re.compile(sys.argv[1]) if len(sys.argv) > 1 else None
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
-cols = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "FFMA2", "MUFU.TANH", "MUFU.EX2", "MUFU.COS"]
+cols = ["UTCHMMA", "HMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "FFMA2", "MUFU.TANH", "MUFU.EX2", "MUFU.COS"]
 counts = collections.OrderedDict()
 cur = None
 for line in sass.splitlines():
@@ -22,7 +22,7 @@ for line in sass.splitlines():
     if cur is None:
         continue
     for c in cols:
-        if re.search(r"\b" + re.escape(c) + r"\b", line):
+        if re.search(r"(?<![A-Z])" + re.escape(c) + r"\b", line):
             cur[c] += 1
 print("| kernel | " + " | ".join(cols) + " |\n|---|" + "---|" * len(cols))
 for name, c in sorted(counts.items()):
