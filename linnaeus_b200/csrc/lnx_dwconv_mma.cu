@@ -176,9 +176,23 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 1)
 
   Item cur = item_of(it_begin, tiles_w, tiles_h, B);
   Item prev = cur;
+  auto claim_out = [&](int n, const Item& c) {  // staging tile n & 1 may be written for the CTA's n-th item (after its skip gradient has landed)
+    if (has_res) {
+      mbar_expect_tx(&outfree[n & 1], res_bytes);
+      tma_load_4d(outs + (size_t)(n & 1) * out_bytes, &tmR, &outfree[n & 1], c.chunk * CC, c.tw * WT, c.th * TROWS, c.b);
+    } else {
+      mbar_arrive(&outfree[n & 1]);
+    }
+  };
   if (threadIdx.x == 0 && n_my > 0) {
     mbar_expect_tx(&full[0], load_bytes);
     tma_load_4d(tiles, &tmX, &full[0], cur.chunk * CC, cur.tw * WT - 3, cur.th * TROWS - 3, cur.b);
+    claim_out(0, cur);
+    if (n_my > 1) {
+      Item c1 = cur;
+      item_next(c1, tiles_w, tiles_h, B);
+      claim_out(1, c1);
+    }
   }
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -187,13 +201,14 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 1)
   const int P = 2 * g * RP + t;
   const int nunits = nxb * 4;
   int cur_chunk = -1;
+  int duty = 0;  // the warp whose lane 0 does the per-item TMA chores: it rotates, so no warp lags behind the others item after item
   for (int it = 0; it < n_my; ++it) {
     Item nxt = cur;
     item_next(nxt, tiles_w, tiles_h, B);
     const int buf = it & 1;
-    if (threadIdx.x == 0) {
+    if (warp == duty && lane == 0) {
       if (it >= 1) {  // item it-1 is complete in its staging tile: send it off
-        mbar_wait_relaxed(&empty[buf ^ 1], (((uint32_t)(it - 1)) >> 1) & 1u);
+        mbar_wait(&empty[buf ^ 1], (((uint32_t)(it - 1)) >> 1) & 1u);
         if (!(dbg & 2)) tma_store_4d(&tmY, outs + (size_t)(buf ^ 1) * out_bytes, prev.chunk * CC, prev.tw * WT, prev.th * TROWS, prev.b);
         bulk_commit_group();
       }
@@ -201,14 +216,12 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 1)
         mbar_expect_tx(&full[buf ^ 1], load_bytes);
         tma_load_4d(tiles + (size_t)(buf ^ 1) * tile_bytes, &tmX, &full[buf ^ 1], nxt.chunk * CC, nxt.tw * WT - 3, nxt.th * TROWS - 3, nxt.b);
       }
-      if (it >= 1) bulk_wait_group_read<1>();  // the store of item it-2 has left this item's staging tile
-      if (has_res) {
-        mbar_expect_tx(&outfree[buf], res_bytes);
-        tma_load_4d(outs + (size_t)buf * out_bytes, &tmR, &outfree[buf], cur.chunk * CC, cur.tw * WT, cur.th * TROWS, cur.b);
-      } else {
-        mbar_arrive(&outfree[buf]);
+      if (it >= 1) {
+        bulk_wait_group_read<0>();  // the store just issued has been read out of its staging tile: hand the tile to item it+1
+        if (it + 1 < n_my) claim_out(it + 1, nxt);
       }
     }
+    duty = duty + 1 == NW ? 0 : duty + 1;
     const int c0 = cur.chunk * CC;
     if (cur.chunk != cur_chunk) {  // uniform over the CTA
       cur_chunk = cur.chunk;
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 1)
   }
   if (threadIdx.x == 0 && n_my > 0) {
     const int lb = (n_my - 1) & 1;
-    mbar_wait_relaxed(&empty[lb], (((uint32_t)(n_my - 1)) >> 1) & 1u);
+    mbar_wait(&empty[lb], (((uint32_t)(n_my - 1)) >> 1) & 1u);
     if (!(dbg & 2)) tma_store_4d(&tmY, outs + (size_t)lb * out_bytes, prev.chunk * CC, prev.tw * WT, prev.th * TROWS, prev.b);
     bulk_commit_group();
     bulk_wait_group_all();
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(WG_WARPS * 32, 1)
                                       // image are never visited); the dy band starts six padded rows = three image rows higher
     const int buf = n & 1;
     unsigned char* st = smem + (size_t)buf * stage_bytes;
-    mbar_wait_relaxed(&empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
+    mbar_wait(&empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
     mbar_expect_tx(&full[buf], in_load + g_load);
     tma_load_4d(st, &tmX, &full[buf], c.chunk * CC, -3, y0, c.b);
     tma_load_4d(st + in_bytes, &tmG, &full[buf], c.chunk * CC, 0, y0 - 3, c.b);
