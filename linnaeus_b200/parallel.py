@@ -34,13 +34,20 @@ class _Bucket:
         self.streams = {}  # stream id -> last "gradient written" event of every CUDA stream that produced gradients of this bucket
 
 
-def plan_buckets(groups: list[FlatGroup], bucket_bytes: int) -> tuple[list[_Bucket], dict[int, int]]:
+def plan_buckets(groups: list[FlatGroup], bucket_bytes: int, first_bucket_bytes: int | None = None) -> tuple[list[_Bucket], dict[int, int]]:
     """Cut each flat group into contiguous buckets of about ``bucket_bytes``; returns the
-    buckets and a map id(param) -> bucket index."""
+    buckets and a map id(param) -> bucket index.
+
+    The FIRST bucket of a group (the first-registered parameters: the stem and the convolutional stages) is the last one whose
+    gradients become final, so its all-reduce can overlap nothing: it is kept small (``first_bucket_bytes``, default a quarter of
+    ``bucket_bytes``) so that the exposed collective at the end of backward is latency- rather than bandwidth-sized -- the mirror image
+    of torch DDP's small first bucket (there: the first gradients READY, to start communicating early)."""
     buckets, owner = [], {}
-    cap = max(1, bucket_bytes // 4)
+    full_cap = max(1, bucket_bytes // 4)
+    first_cap = max(1, (bucket_bytes // 4 if first_bucket_bytes is None else first_bucket_bytes) // 4)
     for gi, g in enumerate(groups):
         lo, count = 0, 0
+        cap = min(first_cap, full_cap)
         for i, p in enumerate(g.params):
             a, b = g.span(i)
             end = g.offsets[i + 1] if i + 1 < len(g.params) else g.numel  # next tensor's (aligned) start
@@ -50,6 +57,7 @@ def plan_buckets(groups: list[FlatGroup], bucket_bytes: int) -> tuple[list[_Buck
             if end - lo >= cap or last:
                 buckets.append(_Bucket(gi, lo, g.numel if last else end, count))
                 lo, count = end, 0
+                cap = full_cap
     return buckets, owner
 
 

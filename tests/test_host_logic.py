@@ -121,3 +121,11 @@ def test_flat_group_and_bucket_plan():
     assert buckets[0].lo == 0 and buckets[-1].hi == g.numel
     for a, b in zip(buckets[:-1], buckets[1:]):
         assert a.hi == b.lo
+    # the first bucket (last to become final in backward: nothing left to overlap its all-reduce with) is cut small
+    qs = [torch.nn.Parameter(torch.randn(64)) for _ in range(32)]
+    g2 = FlatGroup(qs, with_state=False)
+    b2, _ = plan_buckets([g2], bucket_bytes=64 * 4 * 8)
+    sizes = [b.hi - b.lo for b in b2]
+    assert sizes[0] == 64 * 2 and all(s == 64 * 8 for s in sizes[1:-1]) and sum(sizes) == g2.numel
+    b3, _ = plan_buckets([g2], bucket_bytes=64 * 4 * 8, first_bucket_bytes=64 * 4 * 8)
+    assert b3[0].hi - b3[0].lo == 64 * 8
