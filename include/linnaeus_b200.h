@@ -96,6 +96,9 @@ int lnx_layernorm_bwd(const void* dy, const void* x, const float* w, const float
 /* w_layout: LNX_DW_W_TAP_MAJOR = [49, C]; LNX_DW_W_NATIVE = the Conv2d weight itself, [C,1,7,7] = [C, 49]; LNX_DW_W_NATIVE_FLIPPED =
  * the same memory read with the taps reversed.  bias may be NULL.  The data gradient is the same call on dY with the taps reversed
  * and bias = NULL; `residual` (nullable) is added to the result (the skip-connection gradient when run as the data gradient).
+ * bf16: the default kernels run on the tensor pipe (banded matrix products, lnx_dwconv_mma.cu): the weights are rounded to bf16 for
+ * the multiply (as the reference's autocast Conv2d does), accumulation is fp32; a non-finite input spreads over the 16-column K
+ * window it falls in (never to another channel or image).  fp32 and lnx_dwconv7_set_impl(0): fp32 weights, exact 7 x 7 support.
  * R/models/blocks/convnext.py:56-58,76. */
 enum { LNX_DW_W_TAP_MAJOR = 0, LNX_DW_W_NATIVE = 1, LNX_DW_W_NATIVE_FLIPPED = 2 };
 int lnx_dwconv7_fwd(const void* x, const float* w, int w_layout, const float* bias, const void* residual, void* y, int B, int H, int W, int C,
