@@ -139,7 +139,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
 
 __global__ void __launch_bounds__(FWD_WARPS * 32, 1)
     dwconv7_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-                           const float* __restrict__ w, const float* __restrict__ bias, int has_res, int B, int C, int tiles_w, int tiles_h, int WT,
+                           const float* __restrict__ w, const float* __restrict__ bias, int has_res, int B, int W, int C, int tiles_w, int tiles_h, int WT,
                            int RP, int nxb, int wl, int tile_bytes, int out_bytes, int dbg) {
   constexpr int NW = FWD_WARPS;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -199,7 +199,6 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 1)
   const int e = t - g + 7;
   const int hRP = RP >> 1;
   const int P = 2 * g * RP + t;
-  const int nunits = nxb * 4;
   int cur_chunk = -1;
   int duty = 0;  // the warp whose lane 0 does the per-item TMA chores: it rotates, so no warp lags behind the others item after item
   for (int it = 0; it < n_my; ++it) {
@@ -248,8 +247,10 @@ __global__ void __launch_bounds__(FWD_WARPS * 32, 1)
     const uint32_t tile_s = tiles_s + (uint32_t)buf * (uint32_t)tile_bytes;
     const uint32_t out_s = outs_s + (uint32_t)buf * (uint32_t)out_bytes;
 
-    for (int u = warp; u < nunits; u += NW) {
-      const int j = u % nxb, cg = u / nxb;
+    // column blocks of this item: the last column tile of an image may be narrower than WT (W = 56: tiles of 32 + 24 columns)
+    const int nxb_it = min(nxb, (W - prev.tw * WT + 7) >> 3);
+    for (int u = warp; u < nxb_it * 4; u += NW) {
+      const int j = u % nxb_it, cg = u / nxb_it;
       float acc[8][4];
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
@@ -507,7 +508,7 @@ int lnx_dwconv7_fwd_mma(const void* x, const float* w, int wl, const float* bias
                         cudaStream_t st) {
   if (C % CC != 0) return LNX_ERR_SHAPE;
   const int tiles_w = (W + 31) / 32;
-  const int WT = tiles_w == 1 ? W : ((W + tiles_w - 1) / tiles_w + 3) / 4 * 4;
+  const int WT = tiles_w == 1 ? W : 32;  // full 32-column tiles + one narrower last tile: no column block is computed for nothing
   const int RP = round_up_mod(WT + 6, 4, 2);  // 2 mod 4: two tile rows apart = 4 pixels mod 8 (bank-conflict-free quads)
   const int nxb = (WT + 7) / 8;
   const int tiles_h = (H + TROWS - 1) / TROWS;
@@ -527,7 +528,7 @@ int lnx_dwconv7_fwd_mma(const void* x, const float* w, int wl, const float* bias
   static const int dbg = getenv("LNX_DW_DBG") ? atoi(getenv("LNX_DW_DBG")) : 0;  // profiling ablation: 2 = no output stores
   const long long n_items = (long long)B * tiles_h * tiles_w * (C / CC);
   const int grid = (int)(n_items < kNumSMs ? n_items : kNumSMs);
-  dwconv7_fwd_mma_kernel<<<grid, FWD_WARPS * 32, smem, st>>>(tmX, tmY, tmR, w, bias, res ? 1 : 0, B, C, tiles_w, tiles_h, WT, RP, nxb, wl, tile_bytes,
+  dwconv7_fwd_mma_kernel<<<grid, FWD_WARPS * 32, smem, st>>>(tmX, tmY, tmR, w, bias, res ? 1 : 0, B, W, C, tiles_w, tiles_h, WT, RP, nxb, wl, tile_bytes,
                                                              out_bytes, dbg);
   LNX_CHECK_LAUNCH();
   return LNX_OK;
